@@ -1,0 +1,179 @@
+/*
+ * TEST INFRASTRUCTURE ONLY.  CPU restatement (plain C, float64) of the reference's CTC hot path.
+ *
+ * Nothing in the product path (end2end_b200/, pytorch_end2end/) may include, link, import or
+ * execute this file.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs use it, and only as the checker / the reported CPU baseline.
+ *
+ * Parity status: PINNED.  oracle/test vectors: the five known-answer losses of the reference's
+ * tests/test_ctc.py:69-165, the greedy known answers of tests/test_ctc_decoder.py:44-59,86-166,
+ * and differential runs against the compiled, unmodified reference (oracle/_ref, built by
+ * oracle/build_ref.py) -- see tests/test_oracle.py and tests/golden/.
+ *
+ * What is restated (reference file:line):
+ *   lse2()                 <- src/utils/math_utils.h:8-16      two-argument log-sum-exp, -inf guards,
+ *                                                              max + log(1 + exp(min - max))
+ *   ctc_oracle_utterance() <- src/losses/ctc_loss.cpp:15-118   blank-extended labels (:25-31),
+ *                                                              alpha (:33-61), loss (:63-70),
+ *                                                              beta (:72-100), gradient (:102-117)
+ *   ctc_oracle_batch()     <- src/losses/forward_backward.cpp:7-59  per-utterance driver (the
+ *                                                              reference's one-thread-per-utterance
+ *                                                              pool becomes a plain loop / OpenMP)
+ *   ctc_oracle_greedy()    <- src/decoders/ctc_decoder.cpp:443-490  argmax (first maximum, NaN is
+ *                                                              maximal -- torch's rule) then
+ *                                                              collapse repeats / drop blanks
+ *   ctc_oracle_log_softmax_f32() <- pytorch_end2end/modules/ctc_loss.py:40 (F.log_softmax, fp32)
+ *
+ * Storage is frame-major ([T][S]) here, where the reference keeps [S][T]; the arithmetic and the
+ * order of the chained two-argument log-sum-exp calls are the reference's.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define NEG_INF (-INFINITY)
+
+static double lse2(double a, double b) {
+  if (a == NEG_INF) return b;
+  if (b == NEG_INF) return a;
+  if (a > b) return a + log(1.0 + exp(b - a));
+  return b + log(1.0 + exp(a - b));
+}
+
+static int imax(int a, int b) { return a > b ? a : b; }
+static int imin(int a, int b) { return a < b ? a : b; }
+
+/*
+ * One utterance.  lp: [T_pad][V] log-probabilities (row stride V); frames >= T belong to padding.
+ * grad: [T_pad][V], receives exp(lp) - exp(label-summed alpha+beta - logZ) on ALL T_pad rows
+ * (padding rows therefore hold exp(lp); an infeasible utterance gives NaN everywhere), as the
+ * reference does (src/losses/ctc_loss.cpp:105-117).  Returns the loss.
+ */
+double ctc_oracle_utterance(const double* lp, int T_pad, int V, const int64_t* labels, int T, int L,
+                            int blank, double* grad) {
+  const int S = 2 * L + 1;
+  int64_t* ext = (int64_t*)malloc(sizeof(int64_t) * (size_t)S);
+  double* alpha = (double*)malloc(sizeof(double) * (size_t)S * (size_t)T);
+  double* beta = (double*)malloc(sizeof(double) * (size_t)S * (size_t)T);
+  double* psum = (double*)malloc(sizeof(double) * (size_t)T_pad * (size_t)V);
+  for (int s = 0; s < S; s++) ext[s] = (s & 1) ? labels[s / 2] : (int64_t)blank;
+  for (size_t i = 0; i < (size_t)S * T; i++) alpha[i] = beta[i] = NEG_INF;
+  for (size_t i = 0; i < (size_t)T_pad * V; i++) psum[i] = NEG_INF;
+#define A(t, s) alpha[(size_t)(t) * S + (s)]
+#define Bt(t, s) beta[(size_t)(t) * S + (s)]
+#define LP(t, v) lp[(size_t)(t) * V + (v)]
+
+  /* alpha, ctc_loss.cpp:39-61 */
+  if (T > 1 || S == 1) A(0, 0) = LP(0, ext[0]);
+  if (S > 1) A(0, 1) = LP(0, ext[1]);
+  for (int t = 1; t < T; t++) {
+    const int lo = imax(0, S - 2 * (T - t)), hi = imin(2 * t + 2, S);
+    for (int s = lo; s < hi; s++) {
+      double a = A(t - 1, s);
+      if (s > 0) {
+        a = lse2(a, A(t - 1, s - 1));
+        if (ext[s] != blank && s >= 2 && ext[s - 2] != ext[s]) a = lse2(a, A(t - 1, s - 2));
+      }
+      A(t, s) = a + LP(t, ext[s]);
+    }
+  }
+  /* loss, ctc_loss.cpp:63-70 */
+  double loss;
+  if (S > 1) loss = -lse2(A(T - 1, S - 1), A(T - 1, S - 2));
+  else loss = -A(T - 1, S - 1);
+  const double logz = -loss;
+
+  /* beta (excludes the emission at t), ctc_loss.cpp:72-100 */
+  if (T > 1 || S == 1) Bt(T - 1, S - 1) = 0.0;
+  if (S > 1) Bt(T - 1, S - 2) = 0.0;
+  for (int t = T - 2; t >= 0; t--) {
+    const int lo = imax(0, S - 2 * (T - t)), hi = imin(2 * t + 2, S);
+    for (int s = lo; s < hi; s++) {
+      double b = Bt(t + 1, s) + LP(t + 1, ext[s]);
+      if (s < S - 1) {
+        b = lse2(b, Bt(t + 1, s + 1) + LP(t + 1, ext[s + 1]));
+        if (ext[s] != blank && s + 2 < S && ext[s + 2] != ext[s])
+          b = lse2(b, Bt(t + 1, s + 2) + LP(t + 1, ext[s + 2]));
+      }
+      Bt(t, s) = b;
+    }
+  }
+  /* gradient, ctc_loss.cpp:102-117: label-wise lse of alpha+beta, s outer / t inner */
+  for (int s = 0; s < S; s++)
+    for (int t = 0; t < T; t++) {
+      double* cell = &psum[(size_t)t * V + ext[s]];
+      *cell = lse2(*cell, A(t, s) + Bt(t, s));
+    }
+  for (size_t i = 0; i < (size_t)T_pad * V; i++) grad[i] = exp(lp[i]) - exp(psum[i] - logz);
+#undef A
+#undef Bt
+#undef LP
+  free(ext); free(alpha); free(beta); free(psum);
+  return loss;
+}
+
+/*
+ * Batch driver (forward_backward.cpp:7-59).  lp [B][T][V] float64 contiguous, targets [B][Lmax],
+ * lengths int64.  losses [B], grads [B][T][V].  Returns 0, or -1 on arguments the reference would
+ * read out of bounds on (T_i < 1, T_i > T, L_i > Lmax, label outside [0,V)).
+ */
+int ctc_oracle_batch(const double* lp, int B, int T, int V, const int64_t* targets, int Lmax,
+                     const int64_t* in_len, const int64_t* tgt_len, int blank, double* losses,
+                     double* grads) {
+  for (int b = 0; b < B; b++) {
+    if (in_len[b] < 1 || in_len[b] > T || tgt_len[b] < 0 || tgt_len[b] > Lmax) return -1;
+    for (int i = 0; i < tgt_len[b]; i++)
+      if (targets[(size_t)b * Lmax + i] < 0 || targets[(size_t)b * Lmax + i] >= V) return -1;
+  }
+  if (blank < 0 || blank >= V) return -1;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic)
+#endif
+  for (int b = 0; b < B; b++)
+    losses[b] = ctc_oracle_utterance(lp + (size_t)b * T * V, T, V, targets + (size_t)b * Lmax,
+                                     (int)in_len[b], (int)tgt_len[b], blank,
+                                     grads + (size_t)b * T * V);
+  return 0;
+}
+
+/* fp32 row log-softmax: x - max - log(sum(exp(x - max))), all in float, as torch's CPU kernel
+ * evaluates it (modules/ctc_loss.py:40).  Summation order differs from torch's vectorised loop,
+ * so results agree to an ulp or two, not bitwise. */
+void ctc_oracle_log_softmax_f32(const float* x, int64_t rows, int V, float* out) {
+  for (int64_t r = 0; r < rows; r++) {
+    const float* xr = x + r * V;
+    float m = xr[0];
+    for (int v = 1; v < V; v++) if (xr[v] > m) m = xr[v];
+    float sum = 0.f;
+    for (int v = 0; v < V; v++) sum += expf(xr[v] - m);
+    const float ls = logf(sum);
+    for (int v = 0; v < V; v++) out[r * V + v] = xr[v] - m - ls;
+  }
+}
+
+/*
+ * Greedy decode (ctc_decoder.cpp:443-490).  logits [B][T][V] float64 (the caller widens; argmax
+ * is order-preserving under widening).  argmax = first index of the maximum, a NaN beats any
+ * number and the first NaN wins (torch.argmax).  out [B][T] zero-filled then packed; out_len [B].
+ */
+void ctc_oracle_greedy(const double* logits, int B, int T, int V, const int64_t* in_len, int blank,
+                       int64_t* out, int64_t* out_len) {
+  memset(out, 0, sizeof(int64_t) * (size_t)B * T);
+  for (int b = 0; b < B; b++) {
+    int64_t prev = blank, n = 0;
+    for (int t = 0; t < in_len[b] && t < T; t++) {
+      const double* row = logits + ((size_t)b * T + t) * V;
+      int64_t best = 0;
+      double bv = row[0];
+      if (!isnan(bv))
+        for (int v = 1; v < V; v++) {
+          if (isnan(row[v])) { best = v; break; }
+          if (row[v] > bv) { bv = row[v]; best = v; }
+        }
+      if (best != blank && best != prev) out[(size_t)b * T + n++] = best;
+      prev = best;
+    }
+    out_len[b] = n;
+  }
+}
