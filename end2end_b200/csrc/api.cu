@@ -1,0 +1,372 @@
+// C ABI of libe2e_ctc.so (include/e2e_ctc.h): argument checking, workspace planning, kernel
+// sequencing, and the host-buffer engine.  No torch / pybind11 types cross this boundary.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+namespace e2e {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+static inline size_t elem_size(int dtype) {
+  switch (dtype) {
+    case E2E_F32: return 4;
+    case E2E_BF16: case E2E_F16: return 2;
+    case E2E_F64: return 8;
+  }
+  return 0;
+}
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+constexpr int kMaxTargets = (kMaxLatticeWarps * 32 * 8 - 1) / 2;  // K=8: 3072 cells -> L <= 1535
+constexpr int kMaxAlphabet = 32768;
+
+static int check_desc(const e2e_ctc_desc* d, bool need_targets) {
+  if (!d) { set_error("null descriptor"); return E2E_ERR_INVALID_ARGUMENT; }
+  if (d->batch < 1 || d->max_frames < 1 || d->alphabet < 1) {
+    set_error("bad shape B=%d T=%d V=%d", d->batch, d->max_frames, d->alphabet);
+    return E2E_ERR_INVALID_ARGUMENT;
+  }
+  if (elem_size(d->dtype) == 0) { set_error("bad dtype %d", d->dtype); return E2E_ERR_INVALID_ARGUMENT; }
+  if (d->blank_idx < 0 || d->blank_idx >= d->alphabet) {
+    set_error("blank_idx %d outside [0,%d)", d->blank_idx, d->alphabet);
+    return E2E_ERR_INVALID_ARGUMENT;
+  }
+  if ((d->lengths_itype != E2E_I32 && d->lengths_itype != E2E_I64) ||
+      (d->targets_itype != E2E_I32 && d->targets_itype != E2E_I64)) {
+    set_error("bad index type");
+    return E2E_ERR_INVALID_ARGUMENT;
+  }
+  if (d->alphabet > kMaxAlphabet) {
+    set_error("alphabet %d exceeds this build's limit %d", d->alphabet, kMaxAlphabet);
+    return E2E_ERR_UNSUPPORTED;
+  }
+  if (need_targets) {
+    if (d->max_targets < 0) { set_error("bad max_targets %d", d->max_targets); return E2E_ERR_INVALID_ARGUMENT; }
+    if (d->max_targets > kMaxTargets) {
+      set_error("target length %d exceeds this build's limit %d", d->max_targets, kMaxTargets);
+      return E2E_ERR_UNSUPPORTED;
+    }
+  }
+  return E2E_OK;
+}
+
+bool make_loss_plan(const e2e_ctc_desc& d, LossPlan* p) {
+  const int S = 2 * d.max_targets + 1;
+  int K = env_int("E2E_CTC_CELLS_PER_LANE", 0);
+  if (K != 2 && K != 4 && K != 8) K = (S <= 128) ? 2 : (S <= 1024 ? 4 : 8);
+  while (K < 8 && ((S + K - 1) / K + 31) / 32 > kMaxLatticeWarps) K *= 2;
+  const int NW = ((S + K - 1) / K + 31) / 32;
+  if (NW > kMaxLatticeWarps) return false;
+  p->K = K; p->NW = NW; p->cells = 32 * K * NW; p->lanes = 32 * NW;
+  p->lstride = (d.max_targets + 2 + 1) & ~1;
+  int ring = env_int("E2E_CTC_RING", 16);
+  if (ring != 4 && ring != 8 && ring != 16 && ring != 32) ring = 16;
+  auto smem_of = [&](int r) {
+    return (size_t)r * p->lstride * 8 + 64 * 32 + 33 * 8 + 16 * 8 + 36 * 4 + (size_t)d.max_targets * 4 + 64;
+  };
+  while (ring > 4 && smem_of(ring) > 160 * 1024) ring >>= 1;
+  if (smem_of(ring) > 220 * 1024) return false;
+  p->ring = ring;
+  p->chunk = ring / 4;
+  p->smem = smem_of(ring);
+  const size_t rows = (size_t)d.batch * d.max_frames;
+  size_t off = 0;
+  p->off_status = off; off += 256;
+  p->off_flags = off; off += align256((size_t)d.batch * 4);
+  p->off_stats = off; off += align256(rows * (d.dtype == E2E_F64 ? 16 : 8));
+  p->off_hv = off; off += align256(rows * p->cells * 4);
+  p->off_he = off; off += align256(rows * p->lanes * 4);
+  p->off_post = off; off += align256(rows * p->cells * 4);
+  p->total = off;
+  return true;
+}
+
+static int check_ws(const void* ws, size_t have, size_t need) {
+  if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255)) { set_error("workspace null or not 256-byte aligned"); return E2E_ERR_WORKSPACE; }
+  if (have < need) { set_error("workspace too small: %zu < %zu bytes", have, need); return E2E_ERR_WORKSPACE; }
+  return E2E_OK;
+}
+
+static int loss_forward(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
+                        const void* in_len, const void* tgt_len, void* losses, char* ws, cudaStream_t s) {
+  E2E_CUDA_TRY(cudaMemsetAsync(ws + p.off_status, 0, 256, s));
+  int rc = launch_row_stats(d, logits, ws + p.off_stats, s);
+  if (rc != E2E_OK) return rc;
+  return launch_lattice(d, p, logits, targets, in_len, tgt_len, losses, ws, s);
+}
+
+// ---- host-buffer engine -------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap) return E2E_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    const size_t want = align256(n + n / 8);
+    E2E_CUDA_TRY(cudaMalloc(&p, want));
+    cap = want;
+    return E2E_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace e2e
+
+struct e2e_ctc_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  e2e::DevBuf logits, grads, targets, in_len, tgt_len, losses, ws, decoded, decoded_len;
+  uint64_t h2d = 0, d2h = 0;
+};
+
+using namespace e2e;
+
+extern "C" {
+
+const char* e2e_ctc_version(void) { return "e2e_ctc 0.1.0 (sm_100a, abi 1)"; }
+const char* e2e_last_error_string(void) { return g_err; }
+uint64_t e2e_ctc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int e2e_ctc_get_limits(e2e_ctc_limits* out) {
+  if (!out) { set_error("null limits"); return E2E_ERR_INVALID_ARGUMENT; }
+  out->max_alphabet = kMaxAlphabet;
+  out->max_targets = kMaxTargets;
+  out->abi_version = E2E_CTC_ABI_VERSION;
+  out->sm_arch = 100;
+  return E2E_OK;
+}
+
+size_t e2e_ctc_loss_workspace_bytes(const e2e_ctc_desc* desc) {
+  if (check_desc(desc, true) != E2E_OK) return 0;
+  LossPlan p;
+  if (!make_loss_plan(*desc, &p)) { set_error("no lattice configuration for max_targets=%d", desc->max_targets); return 0; }
+  return p.total;
+}
+
+int e2e_ctc_loss_forward_device(const e2e_ctc_desc* desc, const void* logits, const void* targets,
+                                const void* logits_lengths, const void* targets_lengths, void* losses,
+                                void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  int rc = check_desc(desc, true);
+  if (rc != E2E_OK) return rc;
+  if (!logits || !logits_lengths || !targets_lengths || !losses || (!targets && desc->max_targets > 0)) {
+    set_error("null pointer argument");
+    return E2E_ERR_INVALID_ARGUMENT;
+  }
+  LossPlan p;
+  if (!make_loss_plan(*desc, &p)) { set_error("no lattice configuration for max_targets=%d", desc->max_targets); return E2E_ERR_UNSUPPORTED; }
+  rc = check_ws(workspace, workspace_bytes, p.total);
+  if (rc != E2E_OK) return rc;
+  return loss_forward(*desc, p, logits, targets, logits_lengths, targets_lengths, losses,
+                      reinterpret_cast<char*>(workspace), reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+int e2e_ctc_loss_backward_device(const e2e_ctc_desc* desc, const void* logits, const void* targets,
+                                 const void* logits_lengths, const void* targets_lengths,
+                                 const void* grad_out, int32_t grad_out_count, double host_scale,
+                                 void* grads, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  int rc = check_desc(desc, true);
+  if (rc != E2E_OK) return rc;
+  if (!logits || !logits_lengths || !targets_lengths || !grads || (!targets && desc->max_targets > 0)) {
+    set_error("null pointer argument");
+    return E2E_ERR_INVALID_ARGUMENT;
+  }
+  if (grad_out && grad_out_count != 1 && grad_out_count != desc->batch) {
+    set_error("grad_out_count must be 1 or B");
+    return E2E_ERR_INVALID_ARGUMENT;
+  }
+  LossPlan p;
+  if (!make_loss_plan(*desc, &p)) { set_error("no lattice configuration"); return E2E_ERR_UNSUPPORTED; }
+  rc = check_ws(workspace, workspace_bytes, p.total);
+  if (rc != E2E_OK) return rc;
+  return launch_grad(*desc, p, logits, targets, logits_lengths, targets_lengths, grad_out, grad_out_count,
+                     host_scale, grads, reinterpret_cast<const char*>(workspace),
+                     reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+int e2e_ctc_loss_fwd_bwd_device(const e2e_ctc_desc* desc, const void* logits, const void* targets,
+                                const void* logits_lengths, const void* targets_lengths, void* losses,
+                                void* grads, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  int rc = e2e_ctc_loss_forward_device(desc, logits, targets, logits_lengths, targets_lengths, losses,
+                                       workspace, workspace_bytes, cuda_stream);
+  if (rc != E2E_OK) return rc;
+  return e2e_ctc_loss_backward_device(desc, logits, targets, logits_lengths, targets_lengths, nullptr, 0,
+                                      1.0, grads, workspace, workspace_bytes, cuda_stream);
+}
+
+int e2e_ctc_loss_reduce_device(const void* losses, int32_t dtype, int32_t batch, double scale, void* out,
+                               double* out_f64, void* cuda_stream) {
+  if (!losses || batch < 1 || elem_size(dtype) == 0 || (!out && !out_f64)) {
+    set_error("bad reduce arguments");
+    return E2E_ERR_INVALID_ARGUMENT;
+  }
+  return launch_reduce(losses, dtype, batch, scale, out, out_f64, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+int e2e_ctc_loss_check_device(const void* workspace, int32_t* status_host, void* cuda_stream) {
+  if (!workspace || !status_host) { set_error("null pointer argument"); return E2E_ERR_INVALID_ARGUMENT; }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+  E2E_CUDA_TRY(cudaMemcpyAsync(status_host, workspace, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  E2E_CUDA_TRY(cudaStreamSynchronize(s));
+  return E2E_OK;
+}
+
+size_t e2e_ctc_greedy_workspace_bytes(const e2e_ctc_desc* desc) {
+  if (check_desc(desc, false) != E2E_OK) return 0;
+  return align256((size_t)desc->batch * desc->max_frames * sizeof(int));
+}
+
+int e2e_ctc_greedy_decode_device(const e2e_ctc_desc* desc, const void* logits, const void* logits_lengths,
+                                 int64_t* decoded, int64_t* decoded_lengths, void* workspace,
+                                 size_t workspace_bytes, void* cuda_stream) {
+  int rc = check_desc(desc, false);
+  if (rc != E2E_OK) return rc;
+  if (!logits || !decoded || !decoded_lengths) { set_error("null pointer argument"); return E2E_ERR_INVALID_ARGUMENT; }
+  rc = check_ws(workspace, workspace_bytes, e2e_ctc_greedy_workspace_bytes(desc));
+  if (rc != E2E_OK) return rc;
+  return launch_greedy(*desc, logits, logits_lengths, decoded, decoded_lengths,
+                       reinterpret_cast<char*>(workspace), reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+// ---- engine ---------------------------------------------------------------------------------------
+int e2e_ctc_engine_create(int32_t device, e2e_ctc_engine** out) {
+  if (!out) { set_error("null out pointer"); return E2E_ERR_INVALID_ARGUMENT; }
+  *out = nullptr;
+  int n = 0;
+  E2E_CUDA_TRY(cudaGetDeviceCount(&n));
+  if (device < 0 || device >= n) {
+    set_error("CUDA device %d not present (%d devices); this engine has no CPU fallback", device, n);
+    return E2E_ERR_CUDA;
+  }
+  E2E_CUDA_TRY(cudaSetDevice(device));
+  e2e_ctc_engine* e = new (std::nothrow) e2e_ctc_engine();
+  if (!e) { set_error("out of host memory"); return E2E_ERR_CUDA; }
+  e->device = device;
+  cudaError_t ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+  if (ce != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(ce)); delete e; return E2E_ERR_CUDA; }
+  *out = e;
+  return E2E_OK;
+}
+
+void e2e_ctc_engine_destroy(e2e_ctc_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
+  DevBuf* bufs[] = {&e->logits, &e->grads, &e->targets, &e->in_len, &e->tgt_len, &e->losses, &e->ws, &e->decoded, &e->decoded_len};
+  for (DevBuf* b : bufs) b->release();
+  delete e;
+}
+
+// dense [B,T,V] block in either batch-major or time-major order?
+static bool dense_block(const e2e_ctc_desc& d, int64_t sb, int64_t st) {
+  const int64_t B = d.batch, T = d.max_frames, V = d.alphabet;
+  return (sb == T * V && st == V) || (sb == V && st == B * V) || (B == 1 && st == V) || (T == 1 && sb == V);
+}
+
+int e2e_ctc_engine_loss_host(e2e_ctc_engine* e, const e2e_ctc_desc* desc, const void* logits,
+                             const void* targets, const void* logits_lengths, const void* targets_lengths,
+                             void* losses, void* grads) {
+  if (!e) { set_error("null engine"); return E2E_ERR_INVALID_ARGUMENT; }
+  int rc = check_desc(desc, true);
+  if (rc != E2E_OK) return rc;
+  if (!logits || !logits_lengths || !targets_lengths || !losses || !grads || (!targets && desc->max_targets > 0)) {
+    set_error("null pointer argument");
+    return E2E_ERR_INVALID_ARGUMENT;
+  }
+  const e2e_ctc_desc& d = *desc;
+  if (!dense_block(d, d.logits_stride_b, d.logits_stride_t) || !dense_block(d, d.grads_stride_b, d.grads_stride_t) ||
+      (d.max_targets > 0 && d.targets_stride_b != d.max_targets)) {
+    set_error("host tensors must be dense (batch-major or time-major contiguous)");
+    return E2E_ERR_INVALID_ARGUMENT;
+  }
+  LossPlan p;
+  if (!make_loss_plan(d, &p)) { set_error("no lattice configuration for max_targets=%d", d.max_targets); return E2E_ERR_UNSUPPORTED; }
+  E2E_CUDA_TRY(cudaSetDevice(e->device));
+  const size_t es = elem_size(d.dtype);
+  const size_t n_log = (size_t)d.batch * d.max_frames * d.alphabet * es;
+  const size_t n_tgt = (size_t)d.batch * d.max_targets * (d.targets_itype == E2E_I64 ? 8 : 4);
+  const size_t n_len = (size_t)d.batch * (d.lengths_itype == E2E_I64 ? 8 : 4);
+  const size_t n_loss = (size_t)d.batch * es;
+  if ((rc = e->logits.ensure(n_log)) || (rc = e->grads.ensure(n_log)) || (rc = e->targets.ensure(n_tgt + 8)) ||
+      (rc = e->in_len.ensure(n_len)) || (rc = e->tgt_len.ensure(n_len)) || (rc = e->losses.ensure(n_loss)) ||
+      (rc = e->ws.ensure(p.total)))
+    return rc;
+  cudaStream_t s = e->stream;
+  E2E_CUDA_TRY(cudaMemcpyAsync(e->logits.p, logits, n_log, cudaMemcpyHostToDevice, s));
+  if (n_tgt) E2E_CUDA_TRY(cudaMemcpyAsync(e->targets.p, targets, n_tgt, cudaMemcpyHostToDevice, s));
+  E2E_CUDA_TRY(cudaMemcpyAsync(e->in_len.p, logits_lengths, n_len, cudaMemcpyHostToDevice, s));
+  E2E_CUDA_TRY(cudaMemcpyAsync(e->tgt_len.p, targets_lengths, n_len, cudaMemcpyHostToDevice, s));
+  rc = loss_forward(d, p, e->logits.p, e->targets.p, e->in_len.p, e->tgt_len.p, e->losses.p,
+                    reinterpret_cast<char*>(e->ws.p), s);
+  if (rc != E2E_OK) return rc;
+  rc = launch_grad(d, p, e->logits.p, e->targets.p, e->in_len.p, e->tgt_len.p, nullptr, 0, 1.0, e->grads.p,
+                   reinterpret_cast<const char*>(e->ws.p), s);
+  if (rc != E2E_OK) return rc;
+  E2E_CUDA_TRY(cudaMemcpyAsync(losses, e->losses.p, n_loss, cudaMemcpyDeviceToHost, s));
+  E2E_CUDA_TRY(cudaMemcpyAsync(grads, e->grads.p, n_log, cudaMemcpyDeviceToHost, s));
+  E2E_CUDA_TRY(cudaStreamSynchronize(s));
+  e->h2d = n_log + n_tgt + 2 * n_len;
+  e->d2h = n_loss + n_log;
+  return E2E_OK;
+}
+
+int e2e_ctc_engine_greedy_host(e2e_ctc_engine* e, const e2e_ctc_desc* desc, const void* logits,
+                               const void* logits_lengths, int64_t* decoded, int64_t* decoded_lengths) {
+  if (!e) { set_error("null engine"); return E2E_ERR_INVALID_ARGUMENT; }
+  int rc = check_desc(desc, false);
+  if (rc != E2E_OK) return rc;
+  if (!logits || !decoded || !decoded_lengths) { set_error("null pointer argument"); return E2E_ERR_INVALID_ARGUMENT; }
+  const e2e_ctc_desc& d = *desc;
+  if (!dense_block(d, d.logits_stride_b, d.logits_stride_t)) {
+    set_error("host logits must be dense (batch-major or time-major contiguous)");
+    return E2E_ERR_INVALID_ARGUMENT;
+  }
+  E2E_CUDA_TRY(cudaSetDevice(e->device));
+  const size_t n_log = (size_t)d.batch * d.max_frames * d.alphabet * elem_size(d.dtype);
+  const size_t n_len = (size_t)d.batch * (d.lengths_itype == E2E_I64 ? 8 : 4);
+  const size_t n_dec = (size_t)d.batch * d.max_frames * 8, n_dl = (size_t)d.batch * 8;
+  const size_t n_ws = e2e_ctc_greedy_workspace_bytes(desc);
+  if ((rc = e->logits.ensure(n_log)) || (rc = e->in_len.ensure(n_len)) || (rc = e->decoded.ensure(n_dec)) ||
+      (rc = e->decoded_len.ensure(n_dl)) || (rc = e->ws.ensure(n_ws)))
+    return rc;
+  cudaStream_t s = e->stream;
+  E2E_CUDA_TRY(cudaMemcpyAsync(e->logits.p, logits, n_log, cudaMemcpyHostToDevice, s));
+  if (logits_lengths) E2E_CUDA_TRY(cudaMemcpyAsync(e->in_len.p, logits_lengths, n_len, cudaMemcpyHostToDevice, s));
+  rc = launch_greedy(d, e->logits.p, logits_lengths ? e->in_len.p : nullptr, reinterpret_cast<int64_t*>(e->decoded.p),
+                     reinterpret_cast<int64_t*>(e->decoded_len.p), reinterpret_cast<char*>(e->ws.p), s);
+  if (rc != E2E_OK) return rc;
+  E2E_CUDA_TRY(cudaMemcpyAsync(decoded, e->decoded.p, n_dec, cudaMemcpyDeviceToHost, s));
+  E2E_CUDA_TRY(cudaMemcpyAsync(decoded_lengths, e->decoded_len.p, n_dl, cudaMemcpyDeviceToHost, s));
+  E2E_CUDA_TRY(cudaStreamSynchronize(s));
+  e->h2d = n_log + (logits_lengths ? n_len : 0);
+  e->d2h = n_dec + n_dl;
+  return E2E_OK;
+}
+
+int e2e_ctc_engine_last_traffic(const e2e_ctc_engine* e, uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
+  if (!e) { set_error("null engine"); return E2E_ERR_INVALID_ARGUMENT; }
+  if (h2d_bytes) *h2d_bytes = e->h2d;
+  if (d2h_bytes) *d2h_bytes = e->d2h;
+  return E2E_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,151 @@
+// Shared device/host helpers for the sm_100a CTC kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/e2e_ctc.h"
+
+namespace e2e {
+
+// ------------------------------------------------------------------ workspace layout ----------
+// One forward call leaves everything the backward needs in the caller's workspace.
+struct LossPlan {
+  int K;            // lattice cells per lane (even: cells alternate blank,label)
+  int NW;           // lattice warps per CTA
+  int cells;        // 32*K*NW  >= 2*Lmax+1   (row stride of post / hv)
+  int lanes;        // 32*NW                  (row stride of he)
+  int ring;         // emission ring depth in frames
+  int chunk;        // frames per producer hand-off
+  int lstride;      // doubles per ring frame (Lmax+2 rounded up to even)
+  size_t smem;      // dynamic shared memory of the lattice kernel
+  // byte offsets into the workspace
+  size_t off_status, off_flags, off_stats, off_hv, off_he, off_post, total;
+};
+
+bool make_loss_plan(const e2e_ctc_desc& d, LossPlan* p);
+
+constexpr int kProducerWarps = 4;
+constexpr int kMaxLatticeWarps = 12;  // lattice warps per CTA (keeps the kernel at <=128 registers/thread)
+constexpr int kNegExp = -(1 << 28);  // block exponent of an all-zero lane
+
+// status word bits (device-side argument check)
+constexpr int kBadFrames = 1, kBadTargetLen = 2, kBadLabel = 4;
+// per-utterance flags
+constexpr int kFlagInfeasible = 1, kFlagInvalid = 2;
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define E2E_CUDA_TRY(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t e__ = (expr);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      ::e2e::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return E2E_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+// ------------------------------------------------------------------ device helpers ------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ long long load_index(const void* p, int is64, long long i) {
+  return is64 ? reinterpret_cast<const long long*>(p)[i]
+              : (long long)reinterpret_cast<const int*>(p)[i];
+}
+
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+  using acc_t = float;
+  static __device__ __forceinline__ float load(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ void store(float* p, float v) { *p = v; }
+};
+template <> struct Elem<__nv_bfloat16> {
+  using acc_t = float;
+  static __device__ __forceinline__ float load(const __nv_bfloat16* p) {
+    return __bfloat162float(__ldg(p));
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+template <> struct Elem<__half> {
+  using acc_t = float;
+  static __device__ __forceinline__ float load(const __half* p) { return __half2float(__ldg(p)); }
+  static __device__ __forceinline__ void store(__half* p, float v) { *p = __float2half_rn(v); }
+};
+template <> struct Elem<double> {
+  using acc_t = double;
+  static __device__ __forceinline__ double load(const double* p) { return __ldg(p); }
+  static __device__ __forceinline__ void store(double* p, double v) { *p = v; }
+};
+
+// runtime-typed scalar load (used where the element type is not worth a template parameter)
+__device__ __forceinline__ double load_as_double(const void* base, int dtype, long long idx) {
+  switch (dtype) {
+    case E2E_F32: return (double)__ldg(reinterpret_cast<const float*>(base) + idx);
+    case E2E_BF16: return (double)__bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(base) + idx));
+    case E2E_F16: return (double)__half2float(__ldg(reinterpret_cast<const __half*>(base) + idx));
+    default: return __ldg(reinterpret_cast<const double*>(base) + idx);
+  }
+}
+__device__ __forceinline__ float load_as_float(const void* base, int dtype, long long idx) {
+  switch (dtype) {
+    case E2E_F32: return __ldg(reinterpret_cast<const float*>(base) + idx);
+    case E2E_BF16: return __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(base) + idx));
+    case E2E_F16: return __half2float(__ldg(reinterpret_cast<const __half*>(base) + idx));
+    default: return (float)__ldg(reinterpret_cast<const double*>(base) + idx);
+  }
+}
+__device__ __forceinline__ void store_from_double(void* base, int dtype, long long idx, double v) {
+  switch (dtype) {
+    case E2E_F32: reinterpret_cast<float*>(base)[idx] = (float)v; break;
+    case E2E_BF16: reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn((float)v); break;
+    case E2E_F16: reinterpret_cast<__half*>(base)[idx] = __float2half_rn((float)v); break;
+    default: reinterpret_cast<double*>(base)[idx] = v; break;
+  }
+}
+
+// 2^d as a double; 0 below the normal range, clamped above.
+__device__ __forceinline__ double pow2i(int d) {
+  d = min(d, 1023);
+  const double r = __hiloint2double((d + 1023) << 20, 0);
+  return d < -1022 ? 0.0 : r;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_max_int(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+#endif  // __CUDACC__
+
+// ------------------------------------------------------------------ kernel launchers ----------
+int launch_row_stats(const e2e_ctc_desc& d, const void* logits, void* stats, cudaStream_t s);
+int launch_lattice(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
+                   const void* in_len, const void* tgt_len, void* losses, char* ws, cudaStream_t s);
+int launch_grad(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
+                const void* in_len, const void* tgt_len, const void* grad_out, int grad_out_count,
+                double host_scale, void* grads, const char* ws, cudaStream_t s);
+int launch_reduce(const void* losses, int dtype, int B, double scale, void* out, double* out64,
+                  cudaStream_t s);
+int launch_greedy(const e2e_ctc_desc& d, const void* logits, const void* in_len, int64_t* decoded,
+                  int64_t* decoded_len, char* ws, cudaStream_t s);
+
+}  // namespace e2e

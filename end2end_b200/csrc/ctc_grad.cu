@@ -1,0 +1,184 @@
+// K3 -- logits gradient, and K4 -- loss reduction.
+//
+// K3 replaces the tail of CTCLossEngine::compute_2d (src/losses/ctc_loss.cpp:102-117:
+// grads = exp(lp) - exp(label-summed(alpha+beta) - logZ)), the autograd multiply
+// `grads * grad_output.view(-1,1,1)` (functions/forward_backward.py:34) and -- when the input was
+// raw logits -- the log_softmax backward of modules/ctc_loss.py:40, in ONE pass over the logits:
+//
+//     grad[b,t,v] = scale_b * ( softmax(x[b,t,:])[v] - sum_{s: ext[s]==v} post[b,t,s] )
+//
+// One warp per frame row.  The per-cell posteriors written by the lattice kernel are summed per
+// label with shared-memory atomics into a V-float row (blank cells, half of the lattice, are
+// pre-reduced with a warp shuffle), then the row is written back coalesced together with the
+// softmax term.  Padding rows (t >= T_i) carry exp(lp) for log-prob input (the reference's engine
+// contract) or 0 for fused-logits input (what the reference's log_softmax backward leaves there);
+// an infeasible utterance gets an all-NaN block, padding rows included.
+//
+// HBM traffic: reads logits once, writes grads once (+ the lattice posteriors, which are L2-hot).
+#include "common.cuh"
+
+namespace e2e {
+namespace {
+
+struct GradParams {
+  const void* logits; void* grads; long long sb, st, gsb, gst;
+  const void* stats; const float* post; const int* flags;
+  const void* targets; int tgt_is64; long long ts_b;
+  const void* in_len; const void* tgt_len; int len_is64;
+  const void* grad_out; int grad_out_count; double host_scale;
+  int B, T, V, Lmax, blank, from_logits, cells, rows_per_block;
+};
+
+__device__ __forceinline__ float exp_acc(float x) { return expf(x); }
+__device__ __forceinline__ double exp_acc(double x) { return exp(x); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+ctc_grad_kernel(const GradParams p) {
+  using acc_t = typename Elem<T>::acc_t;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int* s_lab = reinterpret_cast<int*>(smem_raw);
+  float* s_acc = reinterpret_cast<float*>(s_lab + p.Lmax + (p.Lmax & 1));
+
+  const int tiles = (p.T + p.rows_per_block - 1) / p.rows_per_block;
+  const int b = blockIdx.x / tiles;
+  const int t0 = (blockIdx.x % tiles) * p.rows_per_block;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int flag = p.flags[b];
+  int Ti = 0, Li = 0;
+  if (!flag) {
+    Ti = (int)load_index(p.in_len, p.len_is64, b);
+    Li = (int)load_index(p.tgt_len, p.len_is64, b);
+  }
+  const bool any_valid = !flag && t0 < Ti;
+  if (any_valid)
+    for (int i = threadIdx.x; i < Li; i += blockDim.x)
+      s_lab[i] = (int)load_index(p.targets, p.tgt_is64, (long long)b * p.ts_b + i);
+  __syncthreads();
+
+  const int t = t0 + w;
+  if (w >= p.rows_per_block || t >= p.T) return;
+
+  acc_t scale = (acc_t)p.host_scale;
+  if (p.grad_out != nullptr)
+    scale *= Elem<T>::load(reinterpret_cast<const T*>(p.grad_out) + (p.grad_out_count == 1 ? 0 : b));
+
+  const T* x = reinterpret_cast<const T*>(p.logits) + b * p.sb + t * p.st;
+  T* g = reinterpret_cast<T*>(p.grads) + b * p.gsb + t * p.gst;
+  const long long row = (long long)b * p.T + t;
+
+  if (flag) {  // infeasible (or rejected) utterance: NaN block, as -inf - (-inf) gives in the reference
+    for (int v = lane; v < p.V; v += 32) Elem<T>::store(g + v, (acc_t)NAN);
+    return;
+  }
+  if (t >= Ti) {  // padding frame
+    if (p.from_logits) {
+      for (int v = lane; v < p.V; v += 32) Elem<T>::store(g + v, scale * (acc_t)0);
+    } else {
+      for (int v = lane; v < p.V; v += 32) Elem<T>::store(g + v, scale * exp_acc(Elem<T>::load(x + v)));
+    }
+    return;
+  }
+
+  float* acc = s_acc + (size_t)w * p.V;
+  for (int v = lane; v < p.V; v += 32) acc[v] = 0.f;
+  __syncwarp();
+  const int S = 2 * Li + 1;
+  const float* post = p.post + row * p.cells;
+  float blank_part = 0.f;
+  for (int s = lane; s < S; s += 32) {
+    const float pv = __ldcg(post + s);
+    if (s & 1) atomicAdd(&acc[s_lab[s >> 1]], pv);
+    else blank_part += pv;
+  }
+  blank_part = warp_sum(blank_part);
+  if (lane == 0) atomicAdd(&acc[p.blank], blank_part);
+  __syncwarp();
+
+  acc_t m = 0, ls = 0;
+  if (p.from_logits) {
+    m = reinterpret_cast<const acc_t*>(p.stats)[2 * row];
+    ls = reinterpret_cast<const acc_t*>(p.stats)[2 * row + 1];
+  }
+  for (int v = lane; v < p.V; v += 32) {
+    const acc_t xv = Elem<T>::load(x + v);
+    const acc_t first = p.from_logits ? exp_acc((xv - m) - ls) : exp_acc(xv);
+    Elem<T>::store(g + v, scale * (first - (acc_t)acc[v]));
+  }
+}
+
+template <typename T>
+int launch_typed(const GradParams& gp, cudaStream_t s) {
+  GradParams p = gp;
+  const size_t lab_bytes = (size_t)(p.Lmax + (p.Lmax & 1)) * sizeof(int);
+  int rpb = 8;
+  while (rpb > 1 && lab_bytes + (size_t)rpb * p.V * sizeof(float) > 96 * 1024) rpb >>= 1;
+  p.rows_per_block = rpb;
+  const size_t smem = lab_bytes + (size_t)rpb * p.V * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_error("grad: alphabet %d too large for the shared-memory row accumulator", p.V);
+    return E2E_ERR_UNSUPPORTED;
+  }
+  if (smem > 48 * 1024)
+    E2E_CUDA_TRY(cudaFuncSetAttribute(ctc_grad_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tiles = (p.T + rpb - 1) / rpb;
+  ctc_grad_kernel<T><<<(unsigned)(p.B * tiles), 256, smem, s>>>(p);
+  count_launch();
+  E2E_CUDA_TRY(cudaGetLastError());
+  return E2E_OK;
+}
+
+// ---- K4: losses[B] -> scale * sum, fp64 accumulation in a fixed order (deterministic) ----------
+__global__ void __launch_bounds__(256)
+ctc_loss_reduce_kernel(const void* losses, int dtype, int B, double scale, void* out, double* out64) {
+  __shared__ double s[256];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < B; i += 256) a += load_as_double(losses, dtype, i);
+  s[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double r = s[0] * scale;
+    if (out) store_from_double(out, dtype, 0, r);
+    if (out64) { out64[0] = r; out64[1] = (double)B; }  // {partial sum, utterance count} for the all-reduce
+  }
+}
+
+}  // namespace
+
+int launch_grad(const e2e_ctc_desc& d, const LossPlan& pl, const void* logits, const void* targets,
+                const void* in_len, const void* tgt_len, const void* grad_out, int grad_out_count,
+                double host_scale, void* grads, const char* ws, cudaStream_t s) {
+  GradParams p;
+  p.logits = logits; p.grads = grads;
+  p.sb = d.logits_stride_b; p.st = d.logits_stride_t; p.gsb = d.grads_stride_b; p.gst = d.grads_stride_t;
+  p.stats = ws + pl.off_stats;
+  p.post = reinterpret_cast<const float*>(ws + pl.off_post);
+  p.flags = reinterpret_cast<const int*>(ws + pl.off_flags);
+  p.targets = targets; p.tgt_is64 = d.targets_itype == E2E_I64; p.ts_b = d.targets_stride_b;
+  p.in_len = in_len; p.tgt_len = tgt_len; p.len_is64 = d.lengths_itype == E2E_I64;
+  p.grad_out = grad_out; p.grad_out_count = grad_out_count; p.host_scale = host_scale;
+  p.B = d.batch; p.T = d.max_frames; p.V = d.alphabet; p.Lmax = d.max_targets; p.blank = d.blank_idx;
+  p.from_logits = d.from_logits; p.cells = pl.cells; p.rows_per_block = 8;
+  switch (d.dtype) {
+    case E2E_F32: return launch_typed<float>(p, s);
+    case E2E_BF16: return launch_typed<__nv_bfloat16>(p, s);
+    case E2E_F16: return launch_typed<__half>(p, s);
+    case E2E_F64: return launch_typed<double>(p, s);
+  }
+  set_error("grad: unsupported dtype %d", d.dtype);
+  return E2E_ERR_INVALID_ARGUMENT;
+}
+
+int launch_reduce(const void* losses, int dtype, int B, double scale, void* out, double* out64,
+                  cudaStream_t s) {
+  ctc_loss_reduce_kernel<<<1, 256, 0, s>>>(losses, dtype, B, scale, out, out64);
+  count_launch();
+  E2E_CUDA_TRY(cudaGetLastError());
+  return E2E_OK;
+}
+
+}  // namespace e2e

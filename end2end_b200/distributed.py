@@ -1,0 +1,129 @@
+"""Batch-sharded CTC across the GPUs of one node (one process per GPU, torch.distributed / NCCL).
+
+The reference has no multi-device path: its only parallelism is one host thread per utterance
+(src/losses/forward_backward.cpp:36-53), and utterances share nothing.  So the path shards by
+utterance with NO data-path collective: every GPU runs the full kernel pipeline on its own bucket
+and owns those gradient rows.  The single exchange step is the reduction of
+modules/ctc_loss.py:52-56 (``loss.sum()`` / ``loss.mean()``): one all-reduce of the pair
+{local loss sum, local utterance count} (16 bytes) -- a pure-latency NCCL collective over
+NVLink/NVSwitch, launched asynchronously so the gradient kernel does not wait for it when the
+global batch size is known.
+
+``plan_shards`` is the host-side planner: cost-balanced (longest-processing-time-first) buckets,
+each bucket sorted by length so that CTAs scheduled together have similar trip counts.
+"""
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+from torch.autograd import Function
+
+from .engine import CTCLossEngine
+
+
+def utterance_cost(frames, target_len, alphabet):
+    """Relative cost of one utterance: lattice cells (T * (2L+1)) plus the streamed row bytes."""
+    return int(frames) * (2 * int(target_len) + 1) + int(frames) * int(alphabet) // 4
+
+
+def plan_shards(logits_lengths, targets_lengths, alphabet, world_size):
+    """LPT assignment of utterance indices to ``world_size`` buckets.
+
+    Returns ``world_size`` lists of indices into the global batch; every index appears exactly
+    once; within a bucket utterances are ordered by decreasing cost.  Deterministic.
+    """
+    ll = [int(v) for v in torch.as_tensor(logits_lengths).tolist()]
+    tl = [int(v) for v in torch.as_tensor(targets_lengths).tolist()]
+    if len(ll) != len(tl):
+        raise ValueError("length vectors differ in size")
+    if world_size < 1:
+        raise ValueError("world_size must be >= 1")
+    cost = [utterance_cost(a, b, alphabet) for a, b in zip(ll, tl)]
+    order = sorted(range(len(cost)), key=lambda i: (-cost[i], i))
+    buckets = [[] for _ in range(world_size)]
+    load = [0] * world_size
+    for i in order:
+        r = min(range(world_size), key=lambda k: (load[k], len(buckets[k]), k))
+        buckets[r].append(i)
+        load[r] += cost[i]
+    return buckets
+
+
+def take_shard(indices, logits, targets, logits_lengths, targets_lengths, time_major=False):
+    """Slice one rank's bucket out of a global batch (host-side helper for data loaders)."""
+    idx = torch.as_tensor(indices, dtype=torch.int64, device=logits.device)
+    lg = logits.index_select(1 if time_major else 0, idx)
+    return (lg, targets.index_select(0, idx.to(targets.device)),
+            logits_lengths.index_select(0, idx.to(logits_lengths.device)),
+            targets_lengths.index_select(0, idx.to(targets_lengths.device)))
+
+
+class _ShardedLossFunction(Function):
+    @staticmethod
+    def forward(ctx, engine, logits, targets, logits_lengths, targets_lengths, from_logits, mean,
+                group, global_batch):
+        ctx.engine, ctx.mean = engine, mean
+        need_grad = ctx.needs_input_grad[1]
+        B = logits.size(0)
+        if logits.is_cuda:
+            losses, state = engine.forward(logits, targets, logits_lengths, targets_lengths, from_logits)
+            ctx.state, ctx.grads = (state if need_grad else None), None
+            pair = engine.partial_sum(losses)           # fp64 {sum, B} written by the reduce kernel
+        else:
+            losses, grads = engine.compute(logits, targets, logits_lengths, targets_lengths, from_logits)
+            ctx.state, ctx.grads = None, (grads if need_grad else None)
+            pair = torch.stack([losses.double().sum(), torch.tensor(float(B), dtype=torch.float64)])
+        if group is not False and dist.is_available() and dist.is_initialized():
+            dist.all_reduce(pair, op=dist.ReduceOp.SUM, group=group)   # THE collective of this path
+        if global_batch is not None:
+            ctx.inv_n = 1.0 / float(global_batch)
+            total = pair[0] * ctx.inv_n if mean else pair[0]
+        else:
+            ctx.inv_n = 1.0 / pair[1]
+            total = pair[0] * ctx.inv_n if mean else pair[0]
+        return total.to(logits.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        if ctx.mean:
+            if isinstance(ctx.inv_n, float):
+                g, scale = grad_output, ctx.inv_n
+            else:
+                g, scale = grad_output * ctx.inv_n.to(grad_output.dtype), 1.0
+        else:
+            g, scale = grad_output, 1.0
+        if ctx.state is not None:
+            grad = ctx.engine.backward(ctx.state, g, scale)
+        else:
+            grad = ctx.grads * (g.to(ctx.grads.device).reshape(1, 1, 1) * scale)
+        return None, grad, None, None, None, None, None, None, None
+
+
+class ShardedCTCLoss(nn.Module):
+    """CTCLoss over a batch sharded across ranks: same arguments as ``CTCLoss`` plus the process
+    group.  Each rank passes ITS bucket; the returned scalar is the global sum (``reduce=True``) or
+    the global mean (``reduce=True, size_average=True``), identical on every rank; the gradient on
+    each rank is the gradient of that global loss w.r.t. the rank's own logits.
+    With ``reduce`` falsy the local per-utterance losses are returned and nothing is exchanged.
+
+    :param global_batch: total utterances over all ranks, if known; lets the gradient kernel run
+        without waiting for the all-reduce.
+    """
+
+    def __init__(self, size_average=None, reduce=None, after_logsoftmax=False, time_major=False, blank_idx=0,
+                 process_group=None, global_batch=None, engine=None):
+        super().__init__()
+        self._reduce, self._size_average = reduce, size_average
+        self._after_logsoftmax, self._time_major = after_logsoftmax, time_major
+        self._group, self._global_batch = process_group, global_batch
+        self._engine = engine if engine is not None else CTCLossEngine(blank_idx)
+
+    def forward(self, logits, targets, logits_lengths, targets_lengths):
+        if self._time_major:
+            logits = logits.permute(1, 0, 2)
+        if not self._reduce:
+            from .functions.forward_backward import ForwardBackwardLossFunction
+            return ForwardBackwardLossFunction.apply(self._engine, logits, targets, logits_lengths,
+                                                     targets_lengths, not self._after_logsoftmax, None)
+        return _ShardedLossFunction.apply(self._engine, logits, targets, logits_lengths, targets_lengths,
+                                          not self._after_logsoftmax, bool(self._size_average),
+                                          self._group, self._global_batch)

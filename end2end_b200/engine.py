@@ -1,0 +1,344 @@
+"""Host-side engines over the C ABI (include/e2e_ctc.h).
+
+``CTCLossEngine`` is the drop-in for the reference's pybind11 class
+``cpp_ctc_loss.CTCLossEngine(blank_idx)`` (src/losses/ctc_loss_py.cpp:5-17): same constructor
+argument, same ``compute(logits, targets, logits_lengths, targets_lengths) -> (losses, grads)``
+contract (src/losses/forward_backward.cpp:7-59) -- inputs are never mutated, results come back on
+the caller's device in the caller's dtype, padding rows of ``grads`` hold ``exp(lp)``, an
+infeasible utterance gives ``+inf`` / an all-NaN block.  Differences, all deliberate:
+
+* the work runs on the GPU (sm_100a kernels); with CPU tensors the engine copies in and out
+  through the host-buffer entry points and there is NO CPU fallback: without a CUDA device the
+  call raises;
+* out-of-range lengths / labels (undefined behaviour in the reference) raise ``ValueError`` when
+  the length tensors live on the host, and are flagged on the device otherwise;
+* ``forward`` / ``backward`` expose the two halves separately so the autograd Function can apply
+  ``grad_output`` inside the gradient kernel instead of in an extra dense pass.
+
+PyTorch is used for device memory and streams only; every byte of arithmetic happens in
+``libe2e_ctc.so``.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_DTYPES = {torch.float32: _lib.E2E_F32, torch.bfloat16: _lib.E2E_BF16,
+           torch.float16: _lib.E2E_F16, torch.float64: _lib.E2E_F64}
+_ITYPES = {torch.int32: _lib.E2E_I32, torch.int64: _lib.E2E_I64}
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else ctypes.c_void_p(0)
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _as_index(t, device, name):
+    if t.dtype not in _ITYPES:
+        if t.is_floating_point() or t.dtype == torch.bool:
+            raise TypeError("%s must be an integer tensor, got %s" % (name, t.dtype))
+        t = t.to(torch.int64)
+    if t.device != device:
+        t = t.to(device, non_blocking=True)
+    return t
+
+
+def _dense3(x):
+    """True if x[B,T,V] can be addressed as base + b*sb + t*st + v (unit alphabet stride)."""
+    if x.size(2) > 1 and x.stride(2) != 1:
+        return False
+    # expanded (stride-0) views would alias rows of the gradient
+    return all(x.stride(i) > 0 or x.size(i) == 1 for i in (0, 1))
+
+
+class _Problem:
+    """Validated, device-resident view of one batch plus the C descriptor."""
+
+    def __init__(self, blank_idx, logits, targets, logits_lengths, targets_lengths, from_logits, device):
+        if logits.dim() != 3:
+            raise ValueError("logits must be [batch, frames, alphabet], got %s" % (tuple(logits.shape),))
+        if logits.dtype not in _DTYPES:
+            raise TypeError("unsupported logits dtype %s" % logits.dtype)
+        B, T, V = logits.shape
+        if B < 1 or T < 1 or V < 1:
+            raise ValueError("empty logits %s" % (tuple(logits.shape),))
+        if not 0 <= blank_idx < V:
+            raise ValueError("blank_idx %d outside the alphabet [0,%d)" % (blank_idx, V))
+        if targets.dim() != 2 or targets.size(0) != B:
+            raise ValueError("targets must be [batch, max_target_length], got %s" % (tuple(targets.shape),))
+        if logits_lengths.dim() != 1 or logits_lengths.numel() != B or \
+                targets_lengths.dim() != 1 or targets_lengths.numel() != B:
+            raise ValueError("length tensors must have shape [batch]")
+        Lmax = targets.size(1)
+        lim = _lib.limits()
+        if Lmax > lim.max_targets or V > lim.max_alphabet:
+            raise NotImplementedError("this build supports target length <= %d and alphabet <= %d"
+                                      % (lim.max_targets, lim.max_alphabet))
+        # the reference has undefined behaviour on these; reject when it costs no device sync
+        if not logits_lengths.is_cuda and not targets_lengths.is_cuda:
+            ll, tl = logits_lengths.to(torch.int64), targets_lengths.to(torch.int64)
+            if bool((ll < 1).any()) or bool((ll > T).any()):
+                raise ValueError("logits_lengths must be in [1, %d]" % T)
+            if bool((tl < 0).any()) or bool((tl > Lmax).any()):
+                raise ValueError("targets_lengths must be in [0, %d]" % Lmax)
+            if not targets.is_cuda and Lmax > 0:
+                tg = targets.to(torch.int64)
+                valid = torch.arange(Lmax).unsqueeze(0) < tl.unsqueeze(1)
+                if bool(((tg < 0) | (tg >= V))[valid].any()):
+                    raise ValueError("target labels must be in [0, %d)" % V)
+        if not _dense3(logits):
+            logits = logits.contiguous()
+        targets = _as_index(targets, device, "targets")
+        if Lmax > 0 and targets.stride(1) != 1:
+            targets = targets.contiguous()
+        logits_lengths = _as_index(logits_lengths, device, "logits_lengths")
+        targets_lengths = _as_index(targets_lengths, device, "targets_lengths")
+        if logits_lengths.dtype != targets_lengths.dtype:
+            logits_lengths, targets_lengths = logits_lengths.to(torch.int64), targets_lengths.to(torch.int64)
+        self.logits, self.targets = logits, targets
+        self.logits_lengths = logits_lengths.contiguous()
+        self.targets_lengths = targets_lengths.contiguous()
+        self.B, self.T, self.V, self.Lmax = B, T, V, Lmax
+        d = _lib.Desc()
+        d.batch, d.max_frames, d.alphabet, d.max_targets = B, T, V, Lmax
+        d.blank_idx, d.dtype = blank_idx, _DTYPES[logits.dtype]
+        d.targets_itype = _ITYPES[targets.dtype]
+        d.lengths_itype = _ITYPES[self.logits_lengths.dtype]
+        d.from_logits = 1 if from_logits else 0
+        d.logits_stride_b, d.logits_stride_t = logits.stride(0), logits.stride(1)
+        d.grads_stride_b, d.grads_stride_t = logits.stride(0), logits.stride(1)
+        d.targets_stride_b = targets.stride(0) if Lmax > 0 else 0
+        self.desc = d
+        self.workspace = None
+
+    def new_grads(self, pin=False):
+        x = self.logits
+        return torch.empty_strided(x.size(), x.stride(), dtype=x.dtype, device=x.device, pin_memory=pin)
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("end2end_b200 needs a CUDA device (sm_100a): the CTC engine has no CPU fallback")
+
+
+class CTCLossEngine:
+    """Drop-in for ``cpp_ctc_loss.CTCLossEngine`` (src/losses/ctc_loss_py.cpp:5-17)."""
+
+    def __init__(self, blank_idx=0):
+        self.blank_idx = int(blank_idx)
+        self._L = _lib.load()
+        self._host = {}
+
+    # ------------------------------------------------------------------ reference contract ----
+    def compute(self, logits, targets, logits_lengths, targets_lengths, from_logits=False):
+        """(losses[B], grads[B,T,V]) exactly as the reference engine returns them; ``logits`` are
+        log-probabilities unless ``from_logits`` (then log_softmax is fused and ``grads`` is the
+        gradient with respect to the raw logits)."""
+        _require_cuda()
+        logits = logits.detach()
+        if not logits.is_cuda:
+            return self._compute_host(logits, targets, logits_lengths, targets_lengths, from_logits)
+        with torch.cuda.device(logits.device):
+            pb = _Problem(self.blank_idx, logits, targets, logits_lengths, targets_lengths, from_logits, logits.device)
+            losses = torch.empty(pb.B, dtype=logits.dtype, device=logits.device)
+            grads = pb.new_grads()
+            ws = self._workspace(pb)
+            _lib.check(self._L.e2e_ctc_loss_fwd_bwd_device(
+                ctypes.byref(pb.desc), _ptr(pb.logits), _ptr(pb.targets), _ptr(pb.logits_lengths),
+                _ptr(pb.targets_lengths), _ptr(losses), _ptr(grads), _ptr(ws), ws.numel(), _stream(logits.device)))
+        return losses, grads
+
+    # ------------------------------------------------------------------ split halves (device) --
+    def forward(self, logits, targets, logits_lengths, targets_lengths, from_logits=False):
+        """Per-utterance losses [B] and an opaque state for :meth:`backward` (device tensors only)."""
+        _require_cuda()
+        logits = logits.detach()
+        with torch.cuda.device(logits.device):
+            pb = _Problem(self.blank_idx, logits, targets, logits_lengths, targets_lengths, from_logits, logits.device)
+            losses = torch.empty(pb.B, dtype=logits.dtype, device=logits.device)
+            pb.workspace = self._workspace(pb)
+            _lib.check(self._L.e2e_ctc_loss_forward_device(
+                ctypes.byref(pb.desc), _ptr(pb.logits), _ptr(pb.targets), _ptr(pb.logits_lengths),
+                _ptr(pb.targets_lengths), _ptr(losses), _ptr(pb.workspace), pb.workspace.numel(),
+                _stream(logits.device)))
+        return losses, pb
+
+    def backward(self, state, grad_output=None, scale=1.0):
+        """grads[b] = scale * grad_output[b or 0] * d loss_b / d logits, written in one pass."""
+        pb = state
+        dev = pb.logits.device
+        with torch.cuda.device(dev):
+            grads = pb.new_grads()
+            count = 0
+            if grad_output is not None:
+                grad_output = grad_output.detach().to(device=dev, dtype=pb.logits.dtype).contiguous()
+                count = grad_output.numel()
+                if count not in (1, pb.B):
+                    raise ValueError("grad_output must have 1 or batch elements")
+            _lib.check(self._L.e2e_ctc_loss_backward_device(
+                ctypes.byref(pb.desc), _ptr(pb.logits), _ptr(pb.targets), _ptr(pb.logits_lengths),
+                _ptr(pb.targets_lengths), _ptr(grad_output), count, float(scale), _ptr(grads),
+                _ptr(pb.workspace), pb.workspace.numel(), _stream(dev)))
+        return grads
+
+    def reduce(self, losses, scale=1.0):
+        """0-dim ``scale * sum(losses)`` (modules/ctc_loss.py:52-56), fp64 accumulation on the device."""
+        out = torch.empty((), dtype=losses.dtype, device=losses.device)
+        with torch.cuda.device(losses.device):
+            _lib.check(self._L.e2e_ctc_loss_reduce_device(
+                _ptr(losses), _DTYPES[losses.dtype], losses.numel(), float(scale), _ptr(out),
+                ctypes.c_void_p(0), _stream(losses.device)))
+        return out
+
+    def partial_sum(self, losses):
+        """fp64 device tensor ``[sum(losses), len(losses)]`` -- the pair a data-parallel caller
+        all-reduces (one 16-byte collective)."""
+        pair = torch.empty(2, dtype=torch.float64, device=losses.device)
+        with torch.cuda.device(losses.device):
+            _lib.check(self._L.e2e_ctc_loss_reduce_device(
+                _ptr(losses), _DTYPES[losses.dtype], losses.numel(), 1.0, ctypes.c_void_p(0),
+                _ptr(pair), _stream(losses.device)))
+        return pair
+
+    def check(self, state):
+        """Device-side argument check of the forward that produced ``state`` (synchronises)."""
+        st = ctypes.c_int32(0)
+        with torch.cuda.device(state.logits.device):
+            _lib.check(self._L.e2e_ctc_loss_check_device(_ptr(state.workspace), ctypes.byref(st),
+                                                         _stream(state.logits.device)))
+        return st.value
+
+    # ------------------------------------------------------------------ internals --------------
+    def _workspace(self, pb):
+        n = self._L.e2e_ctc_loss_workspace_bytes(ctypes.byref(pb.desc))
+        if n == 0:
+            raise _lib.E2EError(2, self._L.e2e_last_error_string().decode("utf-8", "replace"))
+        return torch.empty(n, dtype=torch.uint8, device=pb.logits.device)
+
+    def _host_engine(self, device):
+        h = self._host.get(device)
+        if h is None:
+            h = _HostEngine(device)
+            self._host[device] = h
+        return h
+
+    def _compute_host(self, logits, targets, logits_lengths, targets_lengths, from_logits):
+        dev = torch.cuda.current_device()
+        cpu = torch.device("cpu")
+        if not (logits.is_contiguous() or logits.permute(1, 0, 2).is_contiguous()):
+            logits = logits.contiguous()
+        pb = _Problem(self.blank_idx, logits, targets, logits_lengths, targets_lengths, from_logits, cpu)
+        if pb.Lmax > 0 and not pb.targets.is_contiguous():
+            pb.targets = pb.targets.contiguous()
+            pb.desc.targets_stride_b = pb.Lmax
+        losses = torch.empty(pb.B, dtype=logits.dtype, pin_memory=True)
+        grads = pb.new_grads(pin=True)
+        h = self._host_engine(dev)
+        _lib.check(self._L.e2e_ctc_engine_loss_host(
+            h.handle, ctypes.byref(pb.desc), _ptr(pb.logits), _ptr(pb.targets), _ptr(pb.logits_lengths),
+            _ptr(pb.targets_lengths), _ptr(losses), _ptr(grads)))
+        return losses, grads
+
+    def last_host_traffic(self):
+        """(h2d_bytes, d2h_bytes) of the last host-tensor call."""
+        h = self._host.get(torch.cuda.current_device())
+        return h.traffic() if h else (0, 0)
+
+
+class _HostEngine:
+    """Owns one ``e2e_ctc_engine`` handle (stream + device staging buffers) per CUDA device."""
+
+    def __init__(self, device):
+        self._L = _lib.load()
+        self.handle = ctypes.c_void_p(0)
+        _lib.check(self._L.e2e_ctc_engine_create(int(device), ctypes.byref(self.handle)))
+
+    def traffic(self):
+        a, b = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        _lib.check(self._L.e2e_ctc_engine_last_traffic(self.handle, ctypes.byref(a), ctypes.byref(b)))
+        return int(a.value), int(b.value)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self._L.e2e_ctc_engine_destroy(self.handle)
+                self.handle = ctypes.c_void_p(0)
+        except Exception:
+            pass
+
+
+class CTCGreedyEngine:
+    """Greedy half of ``cpp_ctc_decoder.CTCDecoder`` (src/decoders/ctc_decoder_py.cpp:25-29,
+    src/decoders/ctc_decoder.cpp:443-490): ``decode_greedy(logits_, logits_lengths_)`` returns
+    ``(decoded_targets[B,T] int64 zero padded, decoded_targets_lengths[B] int64)`` as CPU tensors
+    (the sentences are assembled by the Python wrapper)."""
+
+    def __init__(self, blank_idx=0):
+        self.blank_idx = int(blank_idx)
+        self._L = _lib.load()
+        self._host = {}
+
+    def _desc(self, logits, lengths):
+        if logits.dim() != 3:
+            raise ValueError("logits must be [batch, frames, alphabet]")
+        if logits.dtype not in _DTYPES:
+            raise TypeError("unsupported logits dtype %s" % logits.dtype)
+        B, T, V = logits.shape
+        if B < 1 or T < 1 or V < 1:
+            raise ValueError("empty logits")
+        if not 0 <= self.blank_idx < V:
+            raise ValueError("blank_idx %d outside the alphabet [0,%d)" % (self.blank_idx, V))
+        d = _lib.Desc()
+        d.batch, d.max_frames, d.alphabet, d.max_targets = B, T, V, 0
+        d.blank_idx, d.dtype = self.blank_idx, _DTYPES[logits.dtype]
+        d.targets_itype = _lib.E2E_I64
+        d.lengths_itype = _ITYPES[lengths.dtype] if lengths is not None else _lib.E2E_I64
+        d.logits_stride_b, d.logits_stride_t = logits.stride(0), logits.stride(1)
+        return d
+
+    def decode_greedy_device(self, logits, logits_lengths=None):
+        """Device tensors in, device tensors out (no synchronisation)."""
+        _require_cuda()
+        logits = logits.detach()
+        dev = logits.device
+        if not _dense3(logits):
+            logits = logits.contiguous()
+        if logits_lengths is not None:
+            logits_lengths = _as_index(logits_lengths, dev, "logits_lengths").contiguous()
+        d = self._desc(logits, logits_lengths)
+        B, T = logits.size(0), logits.size(1)
+        with torch.cuda.device(dev):
+            decoded = torch.empty(B, T, dtype=torch.int64, device=dev)
+            lengths = torch.empty(B, dtype=torch.int64, device=dev)
+            ws = torch.empty(self._L.e2e_ctc_greedy_workspace_bytes(ctypes.byref(d)), dtype=torch.uint8, device=dev)
+            _lib.check(self._L.e2e_ctc_greedy_decode_device(
+                ctypes.byref(d), _ptr(logits), _ptr(logits_lengths), _ptr(decoded), _ptr(lengths),
+                _ptr(ws), ws.numel(), _stream(dev)))
+        return decoded, lengths
+
+    def decode_greedy(self, logits_, logits_lengths_=None):
+        _require_cuda()
+        logits = logits_.detach()
+        if logits.is_cuda:
+            decoded, lengths = self.decode_greedy_device(logits, logits_lengths_)
+            return decoded.cpu(), lengths.cpu()
+        if not (logits.is_contiguous() or logits.permute(1, 0, 2).is_contiguous()):
+            logits = logits.contiguous()
+        lengths_in = None
+        if logits_lengths_ is not None:
+            lengths_in = _as_index(logits_lengths_, torch.device("cpu"), "logits_lengths").contiguous()
+        d = self._desc(logits, lengths_in)
+        B, T = logits.size(0), logits.size(1)
+        decoded = torch.empty(B, T, dtype=torch.int64, pin_memory=True)
+        lengths = torch.empty(B, dtype=torch.int64, pin_memory=True)
+        dev = torch.cuda.current_device()
+        h = self._host.get(dev)
+        if h is None:
+            h = self._host[dev] = _HostEngine(dev)
+        _lib.check(self._L.e2e_ctc_engine_greedy_host(h.handle, ctypes.byref(d), _ptr(logits), _ptr(lengths_in),
+                                                      _ptr(decoded), _ptr(lengths)))
+        return decoded, lengths

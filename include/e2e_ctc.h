@@ -1,0 +1,184 @@
+/*
+ * e2e_ctc.h -- C ABI of the B200-native CTC engine (libe2e_ctc.so, sm_100a).
+ *
+ * This is the drop-in boundary for the reference's two pybind11 modules:
+ *
+ *   cpp_ctc_loss.CTCLossEngine(blank_idx).compute(logits, targets, logits_lengths,
+ *       targets_lengths) -> (losses[B], grads[B,T,V])
+ *       reference: src/losses/ctc_loss_py.cpp:5-17, src/losses/forward_backward.h:16-19,
+ *                  src/losses/forward_backward.cpp:7-59, src/losses/ctc_loss.cpp:15-118
+ *   cpp_ctc_decoder.CTCDecoder(...).decode_greedy(logits_, logits_lengths_)
+ *       -> (decoded_targets[B,T] int64, decoded_targets_lengths[B] int64, sentences)
+ *       reference: src/decoders/ctc_decoder_py.cpp:25-29, src/decoders/ctc_decoder.cpp:443-490
+ *
+ * Plain pointers and sizes only; no torch / pybind11 types.  Two flavours of every operation:
+ *
+ *   *_device entry points: all pointers are DEVICE pointers on the current CUDA device, work is
+ *       enqueued on `stream` and the call returns without synchronising.  The callee never
+ *       allocates or frees device memory: the caller passes a workspace of at least
+ *       e2e_ctc_*_workspace_bytes() bytes (256-byte aligned).
+ *   e2e_ctc_engine_* entry points: an engine handle owns a stream, device staging buffers and the
+ *       workspace; pointers are HOST pointers (pinned memory makes the copies asynchronous) and
+ *       the call returns when the results are in the host buffers.  This is the form the
+ *       reference's `engine.compute(cpu tensors)` call maps to.
+ *
+ * Every function returns E2E_OK (0) or an error code; e2e_last_error_string() gives the
+ * thread-local message of the last failure.  inf / NaN results are values, not errors
+ * (an infeasible utterance yields loss = +inf and an all-NaN gradient block, as in the reference).
+ */
+#ifndef E2E_CTC_H_
+#define E2E_CTC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define E2E_CTC_ABI_VERSION 1
+
+enum {
+  E2E_OK = 0,
+  E2E_ERR_INVALID_ARGUMENT = 1, /* bad shape / dtype / null pointer / stride                  */
+  E2E_ERR_UNSUPPORTED = 2,      /* valid, but outside this build's limits (see e2e_ctc_limits) */
+  E2E_ERR_WORKSPACE = 3,        /* workspace too small or misaligned                           */
+  E2E_ERR_CUDA = 4,             /* a CUDA runtime call failed                                  */
+  E2E_ERR_LENGTHS = 5           /* a length / label is outside its legal range (UB in the ref) */
+};
+
+/* element type of logits / losses / grads (the reference returns the caller's dtype:
+ * forward_backward.cpp:55-56).  Arithmetic is fp64 lattice + fp32 transcendentals for
+ * F32/BF16/F16 inputs and fp64 throughout for F64 inputs. */
+enum { E2E_F32 = 0, E2E_BF16 = 1, E2E_F16 = 2, E2E_F64 = 3 };
+/* integer type of targets / lengths (the reference accepts int32 or int64:
+ * forward_backward.cpp:16-19) */
+enum { E2E_I32 = 0, E2E_I64 = 1 };
+
+/* Problem descriptor.  Strides are in ELEMENTS; the innermost (alphabet) stride must be 1, so a
+ * time-major [T,B,V] tensor is read and written in place with stride_b = V, stride_t = B*V
+ * (the reference permutes a view: modules/ctc_loss.py:42-43). */
+typedef struct e2e_ctc_desc {
+  int32_t batch;             /* B                                                             */
+  int32_t max_frames;        /* T  (padded number of frames)                                  */
+  int32_t alphabet;          /* V                                                             */
+  int32_t max_targets;       /* Lmax = width of the targets matrix                            */
+  int32_t blank_idx;         /* blank label, 0 <= blank_idx < V                               */
+  int32_t dtype;             /* E2E_F32 / E2E_BF16 / E2E_F16 / E2E_F64                        */
+  int32_t targets_itype;     /* E2E_I32 / E2E_I64                                             */
+  int32_t lengths_itype;     /* E2E_I32 / E2E_I64 (both length vectors)                       */
+  int32_t from_logits;       /* 1: input is raw logits, log_softmax is fused and grads are the
+                                gradient w.r.t. the logits (CTCLoss(after_logsoftmax=False):
+                                modules/ctc_loss.py:37-40 + autograd of log_softmax);
+                                0: input is log-probabilities, grads = exp(lp) - posterior on all
+                                T rows (the engine contract, ctc_loss.cpp:105-117)             */
+  int32_t reserved0;
+  int64_t logits_stride_b;   /* elements between utterances in logits                         */
+  int64_t logits_stride_t;   /* elements between frames in logits                             */
+  int64_t grads_stride_b;    /* same for the gradient output                                  */
+  int64_t grads_stride_t;
+  int64_t targets_stride_b;  /* elements between rows of targets                              */
+} e2e_ctc_desc;
+
+/* Build limits (so callers can test before calling). */
+typedef struct e2e_ctc_limits {
+  int32_t max_alphabet;      /* largest supported V                                           */
+  int32_t max_targets;       /* largest supported target length per utterance                 */
+  int32_t abi_version;
+  int32_t sm_arch;           /* 100 (sm_100a)                                                 */
+} e2e_ctc_limits;
+
+const char* e2e_ctc_version(void);
+const char* e2e_last_error_string(void);
+int e2e_ctc_get_limits(e2e_ctc_limits* out);
+
+/* ---------------------------------------------------------------- loss, device pointers ---- */
+
+/* Bytes of workspace e2e_ctc_loss_* needs for `desc` (0 on error).  The workspace written by
+ * e2e_ctc_loss_forward_device must stay untouched until e2e_ctc_loss_backward_device has run. */
+size_t e2e_ctc_loss_workspace_bytes(const e2e_ctc_desc* desc);
+
+/* Forward: row statistics (fused log-softmax), alpha/beta lattice, per-utterance losses.
+ * losses: [B] of desc->dtype.  Replaces the alpha/beta/loss part of CTCLossEngine::compute_2d
+ * (ctc_loss.cpp:25-100).  All pointers are required (targets may be NULL iff max_targets == 0). */
+int e2e_ctc_loss_forward_device(const e2e_ctc_desc* desc, const void* logits, const void* targets,
+                                const void* logits_lengths, const void* targets_lengths,
+                                void* losses, void* workspace, size_t workspace_bytes,
+                                void* cuda_stream);
+
+/* Backward: grads[b,t,v] = scale_b * (softmax - posterior)  (ctc_loss.cpp:102-117 fused with
+ * functions/forward_backward.py:34 `grads * grad_output.view(-1,1,1)`).
+ *   grad_out == NULL           : scale_b = host_scale
+ *   grad_out_count == 1        : scale_b = host_scale * grad_out[0]   (reduced loss, 0-dim grad)
+ *   grad_out_count == B        : scale_b = host_scale * grad_out[b]   (per-utterance loss)
+ * grad_out is a device pointer of desc->dtype. */
+int e2e_ctc_loss_backward_device(const e2e_ctc_desc* desc, const void* logits, const void* targets,
+                                 const void* logits_lengths, const void* targets_lengths,
+                                 const void* grad_out, int32_t grad_out_count, double host_scale,
+                                 void* grads, void* workspace, size_t workspace_bytes,
+                                 void* cuda_stream);
+
+/* Forward + backward with scale 1: exactly CTCLossEngine.compute() (ctc_loss_py.cpp:10-16). */
+int e2e_ctc_loss_fwd_bwd_device(const e2e_ctc_desc* desc, const void* logits, const void* targets,
+                                const void* logits_lengths, const void* targets_lengths,
+                                void* losses, void* grads, void* workspace, size_t workspace_bytes,
+                                void* cuda_stream);
+
+/* out[0] = scale * sum_b losses[b]  (modules/ctc_loss.py:52-56: sum, or mean with scale = 1/B;
+ * multi-GPU callers all-reduce this scalar).  losses/out are of `dtype`; summation is fp64 in a
+ * fixed order.  out_f64 (optional, may be NULL) points to TWO doubles and receives
+ * {scale * sum, (double)batch}: the pair a data-parallel caller all-reduces across GPUs. */
+int e2e_ctc_loss_reduce_device(const void* losses, int32_t dtype, int32_t batch, double scale,
+                               void* out, double* out_f64, void* cuda_stream);
+
+/* Device-side argument check result of the last forward on this workspace: *status_host = 0 if
+ * every length / label was in range, else a bit mask (1: frames, 2: target length, 4: label).
+ * Synchronises `cuda_stream`. */
+int e2e_ctc_loss_check_device(const void* workspace, int32_t* status_host, void* cuda_stream);
+
+/* --------------------------------------------------------------- greedy decode, device ----- */
+
+size_t e2e_ctc_greedy_workspace_bytes(const e2e_ctc_desc* desc);
+
+/* decoded: [B,T] int64, zero padded; decoded_lengths: [B] int64.  logits_lengths may be NULL
+ * (every utterance decoded over all T frames, decoders/ctc_decoder.py:140-141).
+ * argmax = first maximum, NaN is maximal (torch.argmax, ctc_decoder.cpp:451); then emit a symbol
+ * iff it is not blank and differs from the previous frame's symbol (ctc_decoder.cpp:471-482). */
+int e2e_ctc_greedy_decode_device(const e2e_ctc_desc* desc, const void* logits,
+                                 const void* logits_lengths, int64_t* decoded,
+                                 int64_t* decoded_lengths, void* workspace, size_t workspace_bytes,
+                                 void* cuda_stream);
+
+/* -------------------------------------------------------------- engine, host pointers ------ */
+
+typedef struct e2e_ctc_engine e2e_ctc_engine;
+
+/* Creates an engine bound to CUDA device `device` (fails with E2E_ERR_CUDA when there is no such
+ * device -- there is no CPU fallback). */
+int e2e_ctc_engine_create(int32_t device, e2e_ctc_engine** out);
+void e2e_ctc_engine_destroy(e2e_ctc_engine* engine);
+
+/* Host-buffer form of CTCLossEngine.compute(): copies the inputs to the device, runs the loss
+ * forward+backward there, copies losses [B] and grads back (layout given by desc strides, which
+ * describe the HOST tensors; they must be dense in (t,v) blocks: either batch-major contiguous
+ * or time-major contiguous).  Returns after the results have landed. */
+int e2e_ctc_engine_loss_host(e2e_ctc_engine* engine, const e2e_ctc_desc* desc, const void* logits,
+                             const void* targets, const void* logits_lengths,
+                             const void* targets_lengths, void* losses, void* grads);
+
+/* Host-buffer form of CTCDecoder.decode_greedy(). */
+int e2e_ctc_engine_greedy_host(e2e_ctc_engine* engine, const e2e_ctc_desc* desc, const void* logits,
+                               const void* logits_lengths, int64_t* decoded,
+                               int64_t* decoded_lengths);
+
+/* Bytes moved by the last engine call (for benchmarks): host->device and device->host. */
+int e2e_ctc_engine_last_traffic(const e2e_ctc_engine* engine, uint64_t* h2d_bytes,
+                                uint64_t* d2h_bytes);
+
+/* Number of kernels this library has launched from the calling process since load. */
+uint64_t e2e_ctc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* E2E_CTC_H_ */
