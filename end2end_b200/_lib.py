@@ -21,7 +21,9 @@ EXPORTS = (
     "e2e_ctc_greedy_workspace_bytes", "e2e_ctc_greedy_decode_device",
     "e2e_ctc_engine_create", "e2e_ctc_engine_destroy", "e2e_ctc_engine_loss_host",
     "e2e_ctc_engine_greedy_host", "e2e_ctc_engine_last_traffic", "e2e_ctc_launch_count",
+    "e2e_ctc_profile_enable", "e2e_ctc_profile_read",
 )
+KERNEL_KINDS = ("row_stats", "lattice", "gradient", "loss_reduce", "argmax", "collapse")
 
 
 class Desc(ctypes.Structure):
@@ -84,10 +86,13 @@ def load():
     L.e2e_ctc_engine_greedy_host.argtypes = [vp, dp, vp, vp, vp, vp]
     L.e2e_ctc_engine_last_traffic.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
     L.e2e_ctc_launch_count.restype = ctypes.c_uint64
+    L.e2e_ctc_profile_enable.argtypes = [i32]
+    L.e2e_ctc_profile_read.argtypes = [ctypes.POINTER(dbl), ctypes.POINTER(ctypes.c_uint64), i32]
     for name in ("e2e_ctc_get_limits", "e2e_ctc_loss_forward_device", "e2e_ctc_loss_backward_device",
                  "e2e_ctc_loss_fwd_bwd_device", "e2e_ctc_loss_reduce_device", "e2e_ctc_loss_check_device",
                  "e2e_ctc_greedy_decode_device", "e2e_ctc_engine_create", "e2e_ctc_engine_loss_host",
-                 "e2e_ctc_engine_greedy_host", "e2e_ctc_engine_last_traffic"):
+                 "e2e_ctc_engine_greedy_host", "e2e_ctc_engine_last_traffic", "e2e_ctc_profile_enable",
+                 "e2e_ctc_profile_read"):
         getattr(L, name).restype = ctypes.c_int
     _lib = L
     return L
@@ -102,6 +107,19 @@ def limits():
     lim = Limits()
     check(load().e2e_ctc_get_limits(ctypes.byref(lim)))
     return lim
+
+
+def profile_enable(on=True):
+    check(load().e2e_ctc_profile_enable(1 if on else 0))
+
+
+def profile_read():
+    """{kernel kind: (device ms summed, launches)} since the last read (synchronises)."""
+    n = len(KERNEL_KINDS)
+    ms = (ctypes.c_double * n)()
+    cnt = (ctypes.c_uint64 * n)()
+    check(load().e2e_ctc_profile_read(ms, cnt, n))
+    return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(KERNEL_KINDS)}
 
 
 def launch_count():

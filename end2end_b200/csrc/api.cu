@@ -5,7 +5,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <vector>
 
 #include "common.cuh"
 
@@ -20,7 +22,34 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
-void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+// ---- launch accounting and optional kernel timing --------------------------------------------
+// With profiling on, every kernel launch is bracketed by a pair of CUDA events recorded on the
+// launching stream; e2e_ctc_profile_read() resolves them.  Off (default): one relaxed atomic add.
+struct EventPair { cudaEvent_t a, b; int kind; };
+static std::mutex g_prof_mu;
+static std::atomic<int> g_prof_on{0};
+static std::vector<EventPair> g_prof_pending;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_free;
+static thread_local EventPair t_open{nullptr, nullptr, -1};
+
+void launch_begin(int kind, cudaStream_t s) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  EventPair ev{nullptr, nullptr, kind};
+  if (!g_prof_free.empty()) { ev.a = g_prof_free.back().first; ev.b = g_prof_free.back().second; g_prof_free.pop_back(); }
+  else if (cudaEventCreate(&ev.a) != cudaSuccess || cudaEventCreate(&ev.b) != cudaSuccess) return;
+  cudaEventRecord(ev.a, s);
+  t_open = ev;
+}
+void launch_end(int kind, cudaStream_t s) {
+  if (t_open.kind != kind || !t_open.a) return;
+  cudaEventRecord(t_open.b, s);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_pending.push_back(t_open);
+  t_open = EventPair{nullptr, nullptr, -1};
+}
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 static inline size_t elem_size(int dtype) {
@@ -146,6 +175,27 @@ extern "C" {
 const char* e2e_ctc_version(void) { return "e2e_ctc 0.1.0 (sm_100a, abi 1)"; }
 const char* e2e_last_error_string(void) { return g_err; }
 uint64_t e2e_ctc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int e2e_ctc_profile_enable(int32_t on) {
+  g_prof_on.store(on ? 1 : 0, std::memory_order_relaxed);
+  return E2E_OK;
+}
+
+int e2e_ctc_profile_read(double* ms, uint64_t* launches, int32_t n_kinds) {
+  if (!ms || !launches || n_kinds < kNumKernels) { set_error("profile_read needs %d slots", (int)kNumKernels); return E2E_ERR_INVALID_ARGUMENT; }
+  for (int i = 0; i < n_kinds; i++) { ms[i] = 0.0; launches[i] = 0; }
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (EventPair& ev : g_prof_pending) {
+    E2E_CUDA_TRY(cudaEventSynchronize(ev.b));
+    float t = 0.f;
+    E2E_CUDA_TRY(cudaEventElapsedTime(&t, ev.a, ev.b));
+    ms[ev.kind] += (double)t;
+    launches[ev.kind] += 1;
+    g_prof_free.emplace_back(ev.a, ev.b);
+  }
+  g_prof_pending.clear();
+  return E2E_OK;
+}
 
 int e2e_ctc_get_limits(e2e_ctc_limits* out) {
   if (!out) { set_error("null limits"); return E2E_ERR_INVALID_ARGUMENT; }

@@ -36,7 +36,16 @@ constexpr int kBadFrames = 1, kBadTargetLen = 2, kBadLabel = 4;
 constexpr int kFlagInfeasible = 1, kFlagInvalid = 2;
 
 void set_error(const char* fmt, ...);
-void count_launch(int n = 1);
+
+// Launch accounting + optional per-kernel device timing (CUDA events on the launching stream).
+enum { kKernelRowStats = 0, kKernelLattice, kKernelGrad, kKernelReduce, kKernelArgmax, kKernelCollapse, kNumKernels };
+void launch_begin(int kind, cudaStream_t s);
+void launch_end(int kind, cudaStream_t s);
+struct KernelTimer {   // brackets exactly one kernel launch
+  int kind; cudaStream_t s;
+  KernelTimer(int k, cudaStream_t st) : kind(k), s(st) { launch_begin(k, st); }
+  ~KernelTimer() { launch_end(kind, s); }
+};
 
 #define E2E_CUDA_TRY(expr)                                                              \
   do {                                                                                  \

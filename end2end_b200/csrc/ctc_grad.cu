@@ -122,8 +122,8 @@ int launch_typed(const GradParams& gp, cudaStream_t s) {
   if (smem > 48 * 1024)
     E2E_CUDA_TRY(cudaFuncSetAttribute(ctc_grad_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tiles = (p.T + rpb - 1) / rpb;
+  KernelTimer timer(kKernelGrad, s);
   ctc_grad_kernel<T><<<(unsigned)(p.B * tiles), 256, smem, s>>>(p);
-  count_launch();
   E2E_CUDA_TRY(cudaGetLastError());
   return E2E_OK;
 }
@@ -175,8 +175,8 @@ int launch_grad(const e2e_ctc_desc& d, const LossPlan& pl, const void* logits, c
 
 int launch_reduce(const void* losses, int dtype, int B, double scale, void* out, double* out64,
                   cudaStream_t s) {
+  KernelTimer timer(kKernelReduce, s);
   ctc_loss_reduce_kernel<<<1, 256, 0, s>>>(losses, dtype, B, scale, out, out64);
-  count_launch();
   E2E_CUDA_TRY(cudaGetLastError());
   return E2E_OK;
 }

@@ -95,10 +95,10 @@ template <typename T>
 int launch_typed(const e2e_ctc_desc& d, const void* logits, const void* in_len, int* sym, cudaStream_t s) {
   const long long rows = (long long)d.batch * d.max_frames;
   const unsigned grid = (unsigned)((rows + kRowsPerBlock - 1) / kRowsPerBlock);
+  KernelTimer timer(kKernelArgmax, s);
   ctc_argmax_kernel<T><<<grid, kRowsPerBlock * 32, 0, s>>>(
       reinterpret_cast<const T*>(logits), d.logits_stride_b, d.logits_stride_t, d.batch, d.max_frames,
       d.alphabet, in_len, d.lengths_itype == E2E_I64, sym);
-  count_launch();
   E2E_CUDA_TRY(cudaGetLastError());
   return E2E_OK;
 }
@@ -117,10 +117,10 @@ int launch_greedy(const e2e_ctc_desc& d, const void* logits, const void* in_len,
     default: set_error("greedy: unsupported dtype %d", d.dtype); return E2E_ERR_INVALID_ARGUMENT;
   }
   if (rc != E2E_OK) return rc;
+  KernelTimer timer(kKernelCollapse, s);
   ctc_collapse_kernel<<<(unsigned)d.batch, 256, 0, s>>>(
       sym, d.max_frames, d.blank_idx, in_len, d.lengths_itype == E2E_I64,
       reinterpret_cast<long long*>(decoded), reinterpret_cast<long long*>(decoded_len));
-  count_launch();
   E2E_CUDA_TRY(cudaGetLastError());
   return E2E_OK;
 }

@@ -70,6 +70,23 @@ __device__ __forceinline__ void cluster_arrive() {
 __device__ __forceinline__ void cluster_wait() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Arrive (release, cluster scope) on the mbarrier at the same shared-memory offset in the peer CTA.
+__device__ __forceinline__ void mbar_arrive_peer(uint64_t* bar, uint32_t peer_rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)), "r"(peer_rank)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, int parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra D_%=;\n\t"
+      "bra W_%=;\n\t"
+      "D_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -184,6 +201,27 @@ __device__ void run_producer(const LatticeParams& p, int b, int Ti, int Li, cons
   }
 }
 
+// ---- block-wide sum of per-lane values v * 2^ex over the Wi lattice warps ---------------------
+// Two-phase: maximum exponent of the non-zero lanes, then the exponent-aligned sum.  Every lane of
+// every active lattice warp must call it (named barrier 1).  Result: total = z * 2^ez.
+__device__ __forceinline__ void block_sum_scaled(double v, int ex, double* s_redd, int* s_redi, int w,
+                                                 int lane, int Wi, double* z, int* ez) {
+  const int nthr = Wi * 32;
+  int emax = warp_max_int(v > 0.0 ? ex : 4 * kNegExp);
+  if (lane == 0) s_redi[w] = emax;
+  chain_barrier(nthr);
+  emax = s_redi[0];
+  for (int q = 1; q < Wi; q++) emax = max(emax, s_redi[q]);
+  const double part = warp_sum(v > 0.0 ? v * pow2i(ex - emax) : 0.0);
+  if (lane == 0) s_redd[w] = part;
+  chain_barrier(nthr);
+  double t = 0.0;
+  for (int q = 0; q < Wi; q++) t += s_redd[q];
+  chain_barrier(nthr);   // the scratch may be reused right away
+  *z = t;
+  *ez = emax;
+}
+
 // ---- one lattice frame for one lane -----------------------------------------------------------
 template <int K, bool BWD>
 __device__ __forceinline__ void lattice_step(double (&x)[K], int& e, int& sh, const double* Erow,
@@ -267,8 +305,9 @@ __device__ __forceinline__ void lattice_step(double (&x)[K], int& e, int& sh, co
 
 template <int K, bool BWD>
 __device__ void run_chain(const LatticeParams& p, int b, int Ti, int Li, const int* s_lab,
-                          const double* s_E, uint64_t* s_full, uint64_t* s_empty, Boundary* s_bnd,
-                          double* s_redd, int* s_redi, const double* s_lsesum, int w, int lane, int Wi) {
+                          const double* s_E, uint64_t* s_full, uint64_t* s_empty, uint64_t* s_meet,
+                          Boundary* s_bnd, double* s_redd, int* s_redi, const double* s_lsesum, int w,
+                          int lane, int Wi) {
   constexpr int H = K / 2;
   constexpr int PF = 4;  // prefetch distance (frames) for the other sweep's stored half
   const int S = 2 * Li + 1;
@@ -306,6 +345,12 @@ __device__ void run_chain(const LatticeParams& p, int b, int Ti, int Li, const i
       for (int j = 0; j < K; j++) if (j == entry % K) x[j] = 1.0;
       e = 0;
     }
+    // publish the virtual frame's boundary cells for step 0 (matters when the entry cell sits on
+    // a warp edge, e.g. the backward entry S-1 landing on lane 0 of a warp)
+    if (Wi > 1) {
+      if (!BWD) { if (lane == 31) { s_bnd[w].x0 = x[K - 1]; s_bnd[w].e = e; } }
+      else { if (lane == 0) { s_bnd[w].x0 = x[0]; s_bnd[w].x1 = x[1]; s_bnd[w].e = e; } }
+    }
   }
 
   const int tm = Ti / 2;
@@ -337,13 +382,18 @@ __device__ void run_chain(const LatticeParams& p, int b, int Ti, int Li, const i
     }
   }
   // ---------------- the halves meet ----------------
-  cluster_arrive();
-  cluster_wait();
+  // Each lattice warp publishes its stored half (its lanes' global stores, ordered by the warp
+  // barrier, released at cluster scope by lane 0's remote arrive) on the PEER CTA's mbarrier and
+  // acquires the peer's half on its own.
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) mbar_arrive_peer(s_meet, BWD ? 0u : 1u);
+  mbar_wait_cluster(s_meet, 0);
   const int ncomb = Ti - nstore;
   if (ncomb == 0) return;
 
   // first combine frame: also yields Z = sum_s alpha(t,s) * beta(t,s)
-  double invz, zfinal;
+  double invz;
   int Ez;
   {
     const int t = BWD ? (Ti - 1 - i) : i;
@@ -367,20 +417,9 @@ __device__ void run_chain(const LatticeParams& p, int b, int Ti, int Li, const i
 #pragma unroll
     for (int j = 0; j < K; j++) { prod[j] = val[j] * unpack_hi32(ov[j]); lsum += prod[j]; }
     const int El = en + oe;
-    // block reduction: maximum exponent of the non-zero lanes, then the aligned sum
-    int emax = warp_max_int(lsum > 0.0 ? El : 4 * kNegExp);
-    if (lane == 0) s_redi[w] = emax;
-    chain_barrier(nthr);
-    emax = s_redi[0];
-    for (int q = 1; q < Wi; q++) emax = max(emax, s_redi[q]);
-    double part = warp_sum(lsum > 0.0 ? lsum * pow2i(El - emax) : 0.0);
-    if (lane == 0) s_redd[w] = part;
-    chain_barrier(nthr);
-    double z = 0.0;
-    for (int q = 0; q < Wi; q++) z += s_redd[q];
-    Ez = emax;
-    invz = 1.0 / z;   // z == 0 (no path survives): +inf -> NaN posteriors, loss = +inf
-    zfinal = z;
+    double z;
+    block_sum_scaled(lsum, El, s_redd, s_redi, w, lane, Wi, &z, &Ez);
+    invz = 1.0 / z;   // z == 0 (no path survives): NaN posteriors; the utterance gets flagged below
     if (lane_active) {
       const double c = pow2i(El - Ez) * invz;
       float po[K];
@@ -435,17 +474,27 @@ __device__ void run_chain(const LatticeParams& p, int b, int Ti, int Li, const i
       }
     }
   }
-  // loss = -log Z (ctc_loss.cpp:63-70).  Emissions were normalised per row, so for log-prob
-  // input the row normalisers (all ~0 for true log-probabilities) are added back.
-  if (!BWD && w == 0 && lane == 0) {
-    double loss = INFINITY;
-    if (zfinal > 0.0) {
-      loss = -(log(zfinal) + (double)Ez * 0.69314718055994530942);
-      if (!p.from_logits) loss -= *s_lsesum;
-    } else {
-      p.flags[b] = kFlagInfeasible;
+  // loss = -log(alpha[S-1][T-1] + alpha[S-2][T-1]) (ctc_loss.cpp:63-70), taken from the LIVE fp64
+  // forward state (not from the 21-bit stored half), so it is accurate to fp64 rounding.
+  // Emissions were normalised per row, so for log-prob input the row normalisers (all ~0 for
+  // true log-probabilities) are added back.
+  if (!BWD) {
+    double tail = 0.0;
+#pragma unroll
+    for (int j = 0; j < K; j++) if (s0 + j == S - 1 || s0 + j == S - 2) tail += x[j];
+    double z;
+    int ez;
+    block_sum_scaled(tail, e, s_redd, s_redi, w, lane, Wi, &z, &ez);
+    if (w == 0 && lane == 0) {
+      double loss = INFINITY;
+      if (z > 0.0) {
+        loss = -(log(z) + (double)ez * 0.69314718055994530942);
+        if (!p.from_logits) loss -= *s_lsesum;
+      } else {
+        p.flags[b] = kFlagInfeasible;
+      }
+      store_from_double(p.losses, p.dtype, b, loss);
     }
-    store_from_double(p.losses, p.dtype, b, loss);
   }
 }
 
@@ -464,6 +513,7 @@ ctc_lattice_kernel(const LatticeParams p) {
   double* s_lsesum = s_redd + 32;
   uint64_t* s_full = reinterpret_cast<uint64_t*>(s_lsesum + 1);
   uint64_t* s_empty = s_full + 8;
+  uint64_t* s_meet = s_empty + 7;   // rings use at most 4 slots of the 8 reserved
   int* s_redi = reinterpret_cast<int*>(s_empty + 8);
   int* s_misc = s_redi + 32;  // [0] argument-check bits, [1] adjacent repeats
   int* s_lab = s_misc + 4;
@@ -517,30 +567,34 @@ ctc_lattice_kernel(const LatticeParams p) {
       mbar_init(&s_full[c], kProducerWarps * 32);
       mbar_init(&s_empty[c], Wi);
     }
+    mbar_init(s_meet, Wi);
     *s_lsesum = 0.0;
   }
   for (int f = tid; f < p.ring; f += blockDim.x) s_E[(size_t)f * p.lstride + Li + 1] = 0.0;
   for (int q = tid; q < 64; q += blockDim.x) { s_bnd[q].x0 = 0.0; s_bnd[q].x1 = 0.0; s_bnd[q].e = kNegExp; }
   __syncthreads();
+  // Both CTAs of the pair took the same early-exit decisions above, so both reach this point:
+  // the peer's mbarriers exist before anyone arrives on them remotely.
+  cluster_arrive();
+  cluster_wait();
 
-  if (w >= NW) {  // emission producers never wait on the cluster barrier
-    cluster_arrive();
+  if (w >= NW) {  // emission producers
     const int ptid = tid - NW * 32;
     if (bwd) run_producer<true>(p, b, Ti, Li, s_lab, s_E, s_full, s_empty, s_lsesum, ptid, kProducerWarps * 32);
     else run_producer<false>(p, b, Ti, Li, s_lab, s_E, s_full, s_empty, s_lsesum, ptid, kProducerWarps * 32);
     return;
   }
-  if (w >= Wi) { cluster_arrive(); return; }
-  if (bwd) run_chain<K, true>(p, b, Ti, Li, s_lab, s_E, s_full, s_empty, s_bnd, s_redd, s_redi, s_lsesum, w, lane, Wi);
-  else run_chain<K, false>(p, b, Ti, Li, s_lab, s_E, s_full, s_empty, s_bnd, s_redd, s_redi, s_lsesum, w, lane, Wi);
+  if (w >= Wi) return;
+  if (bwd) run_chain<K, true>(p, b, Ti, Li, s_lab, s_E, s_full, s_empty, s_meet, s_bnd, s_redd, s_redi, s_lsesum, w, lane, Wi);
+  else run_chain<K, false>(p, b, Ti, Li, s_lab, s_E, s_full, s_empty, s_meet, s_bnd, s_redd, s_redi, s_lsesum, w, lane, Wi);
 }
 
 template <int K>
 int launch_k(const LatticeParams& lp, const LossPlan& p, cudaStream_t s) {
   E2E_CUDA_TRY(cudaFuncSetAttribute(ctc_lattice_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   const unsigned threads = 32u * (unsigned)(p.NW + kProducerWarps);
+  KernelTimer timer(kKernelLattice, s);
   ctc_lattice_kernel<K><<<2u * (unsigned)lp.B, threads, p.smem, s>>>(lp);
-  count_launch();
   E2E_CUDA_TRY(cudaGetLastError());
   return E2E_OK;
 }

@@ -114,10 +114,10 @@ int launch_typed(const e2e_ctc_desc& d, const void* logits, void* stats, cudaStr
   const bool vec_ok = (reinterpret_cast<uintptr_t>(logits) % vb == 0) &&
                       ((d.logits_stride_b * sizeof(T)) % vb == 0) &&
                       ((d.logits_stride_t * sizeof(T)) % vb == 0) && d.alphabet >= VEC * 8;
+  KernelTimer timer(kKernelRowStats, s);
   ctc_row_stats_kernel<T, VEC><<<grid, kRowsPerBlock * 32, 0, s>>>(
       reinterpret_cast<const T*>(logits), d.logits_stride_b, d.logits_stride_t, d.batch,
       d.max_frames, d.alphabet, vec_ok, reinterpret_cast<typename Elem<T>::acc_t*>(stats));
-  count_launch();
   E2E_CUDA_TRY(cudaGetLastError());
   return E2E_OK;
 }

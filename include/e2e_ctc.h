@@ -178,6 +178,14 @@ int e2e_ctc_engine_last_traffic(const e2e_ctc_engine* engine, uint64_t* h2d_byte
 /* Number of kernels this library has launched from the calling process since load. */
 uint64_t e2e_ctc_launch_count(void);
 
+/* Optional per-kernel device timing for benchmarks.  While enabled, every kernel launch is
+ * bracketed by CUDA events on its launching stream.  e2e_ctc_profile_read() waits for the pending
+ * events, then fills ms[k] (summed device milliseconds) and launches[k] per kernel kind
+ * k = 0 row_stats, 1 lattice, 2 gradient, 3 loss_reduce, 4 argmax, 5 collapse (n_kinds >= 6),
+ * and clears the record.  All launches since the previous read must have been made on ONE device. */
+int e2e_ctc_profile_enable(int32_t on);
+int e2e_ctc_profile_read(double* ms, uint64_t* launches, int32_t n_kinds);
+
 #ifdef __cplusplus
 }
 #endif

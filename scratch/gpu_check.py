@@ -1,4 +1,5 @@
 import sys, time, os
+import faulthandler; faulthandler.dump_traceback_later(400, exit=True)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import oracle

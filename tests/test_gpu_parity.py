@@ -1,0 +1,444 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).
+
+The CUDA path (through the public modules, the engine, and the raw C ABI) is compared with
+* the golden vectors the reference itself produced (tests/golden, made by make_golden.py),
+* the CPU oracle (the compiled reference when oracle/_ref travelled, else the C port) on the
+  seeded synthetic draws of every BASELINE config at sizes the oracle finishes in seconds,
+* size-independent properties at BASELINE's full sizes.
+
+Tolerances (BASELINE.json north_star): loss and logits-gradient rel 1e-5 / abs 1e-5 in fp32
+(NaN / inf positions must coincide); bf16 logits: fp32-accurate loss (1e-5) and gradients within
+one bf16 ulp (rel 2^-8, abs 1e-5) of the reference run on logits.float(); greedy decodes bit-exact.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL, ATOL = 1e-5, 1e-5
+BF16_RTOL = 2.0 ** -8
+
+
+def gold(name):
+    return np.load(os.path.join(GOLD, name + ".npz"))
+
+
+def T(a):
+    return torch.from_numpy(np.array(a))
+
+
+def assert_parity(ours, ref, rtol=RTOL, atol=ATOL, what=""):
+    ours, ref = ours.detach().cpu().double(), ref.detach().cpu().double()
+    assert ours.shape == ref.shape, (what, ours.shape, ref.shape)
+    assert torch.equal(torch.isnan(ours), torch.isnan(ref)), what + ": NaN positions differ"
+    assert torch.equal(torch.isposinf(ours), torch.isposinf(ref)), what + ": +inf positions differ"
+    fin = torch.isfinite(ref)
+    err = (ours[fin] - ref[fin]).abs()
+    bad = err > atol + rtol * ref[fin].abs()
+    assert not bool(bad.any()), "%s: %d/%d outside tolerance, max abs err %.3e" % (
+        what, int(bad.sum()), err.numel(), float(err.max()))
+
+
+@pytest.fixture(scope="module")
+def e2e():
+    import end2end_b200
+    from end2end_b200 import _lib
+    _lib.load()
+    return end2end_b200
+
+
+def cuda(*ts):
+    return [t.cuda() if t is not None else None for t in ts]
+
+
+# --------------------------------------------------------------------------------------------
+# the reference's own known-answer tests, driven the way tests/test_ctc.py:22-66 drives them
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["simple", "medium", "empty_label", "tf_1", "tf_2"])
+def test_reference_known_answers(e2e, name):
+    g = gold("kat_loss")
+    lp_tm = T(g[name + "_lp"]).permute(1, 0, 2).contiguous()            # time major, as run_grads does
+    tg, ll, tl = T(g[name + "_targets"]), T(g[name + "_ll"]), T(g[name + "_tl"])
+    crit = e2e.CTCLoss(reduce=True, size_average=False, after_logsoftmax=True, time_major=True,
+                       blank_idx=int(g[name + "_blank"]))
+    costs = []
+    for dev in ("cpu", "cuda"):                                        # host-tensor path and device path
+        leaf = lp_tm.to(dev).requires_grad_()
+        cost = crit(leaf, tg, ll, tl)                                   # int32 CPU targets/lengths, as in the reference
+        cost.backward()
+        costs.append(cost.item())
+        assert abs(cost.item() - float(g[name + "_expected"])) < 1e-5   # assertAlmostEqual(places=5)
+        assert_parity(leaf.grad, T(g[name + "_ref_grad_tm"]), what=name + " grad " + dev)
+    assert abs(costs[0] - costs[1]) < 1e-5                              # cpu_cost == gpu_cost
+
+
+# --------------------------------------------------------------------------------------------
+# golden vectors produced by the reference (engine contract + module flag sets)
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c1", "c2_b4", "c2_b4_peaky", "c4_b2", "edge_blank0", "edge_blank3"])
+def test_engine_contract_golden(e2e, name):
+    g = gold(name)
+    lp = torch.log_softmax(T(g["x"]), 2)
+    tg, ll, tl = T(g["targets"]), T(g["logits_lengths"]), T(g["targets_lengths"])
+    eng = e2e.CTCLossEngine(int(g["blank"]))
+    for tensors in ((lp.cuda(), *cuda(tg, ll, tl)), (lp.cuda(), tg, ll, tl), (lp, tg, ll, tl)):
+        losses, grads = eng.compute(*tensors)
+        assert losses.device == tensors[0].device and grads.device == tensors[0].device
+        assert losses.dtype == lp.dtype and grads.shape == lp.shape
+        assert_parity(losses, T(g["engine_losses"]), what=name + " losses")
+        assert_parity(grads, T(g["engine_grads"]), what=name + " grads")   # incl. padding rows = exp(lp), NaN blocks
+
+
+@pytest.mark.parametrize("name", ["c1", "c2_b4", "c2_b4_peaky", "c4_b2", "edge_blank0", "edge_blank3"])
+def test_module_golden(e2e, name):
+    g = gold(name)
+    x = T(g["x"])
+    tg, ll, tl = cuda(T(g["targets"]), T(g["logits_lengths"]), T(g["targets_lengths"]))
+    i = 0
+    while "m%d_flags" % i in g:
+        reduce_, size_average, after, tm = [bool(v) for v in g["m%d_flags" % i]]
+        xin = torch.log_softmax(x, 2) if after else x
+        if tm:
+            xin = xin.permute(1, 0, 2).contiguous()
+        leaf = xin.cuda().requires_grad_()
+        crit = e2e.CTCLoss(reduce=reduce_ or None, size_average=size_average or None, after_logsoftmax=after,
+                           time_major=tm, blank_idx=int(g["blank"]))
+        loss = crit(leaf, tg, ll, tl)
+        (loss.sum() if loss.dim() else loss).backward()
+        assert_parity(loss, T(g["m%d_loss" % i]), what="%s mode %d loss" % (name, i))
+        assert_parity(leaf.grad, T(g["m%d_grad" % i]), what="%s mode %d grad" % (name, i))
+        assert leaf.grad.is_contiguous()
+        i += 1
+    assert i > 0
+
+
+def test_float64_golden_and_gradcheck(e2e):
+    g = gold("f64")
+    x, tg, ll, tl = T(g["x"]), T(g["targets"]), T(g["logits_lengths"]), T(g["targets_lengths"])
+    leaf = x.cuda().requires_grad_()
+    crit = e2e.CTCLoss(blank_idx=0, time_major=False, after_logsoftmax=False)
+    loss = crit(leaf, *cuda(tg, ll, tl))
+    loss.sum().backward()
+    assert loss.dtype == torch.float64
+    assert_parity(loss, T(g["m0_loss"]), rtol=1e-9, atol=1e-9, what="f64 loss")
+    assert_parity(leaf.grad, T(g["m0_grad"]), rtol=1e-6, atol=1e-6, what="f64 grad")
+    # the reference's test_gradient (tests/test_ctc.py:168-191): numerical vs analytic gradient
+    inp = (x.cuda().requires_grad_(), *cuda(tg, ll, tl))
+    assert torch.autograd.gradcheck(crit, inp, eps=1e-6, atol=1e-4, nondet_tol=1e-6)
+
+
+def test_bf16_golden(e2e):
+    g = gold("bf16_c3_b4")
+    xb = T(g["x_bf16_bits"]).view(torch.bfloat16)
+    tg, ll, tl = cuda(T(g["targets"]), T(g["logits_lengths"]), T(g["targets_lengths"]))
+    leaf = xb.cuda().requires_grad_()
+    loss = e2e.CTCLoss(reduce=True, size_average=True)(leaf, tg, ll, tl)
+    loss.backward()
+    assert loss.dtype == torch.bfloat16 and leaf.grad.dtype == torch.bfloat16
+    # bf16-stored outputs: one bf16 ulp of the reference evaluated on logits.float()
+    assert_parity(loss, T(g["m0_loss"]), rtol=BF16_RTOL, atol=ATOL, what="bf16 loss")
+    assert_parity(leaf.grad, T(g["m0_grad"]), rtol=BF16_RTOL, atol=ATOL, what="bf16 grad")
+    # the arithmetic itself is fp32/fp64: same logits widened to fp32 meet the fp32 tolerance
+    leaf32 = xb.float().cuda().requires_grad_()
+    per_utt = e2e.CTCLoss()(leaf32, tg, ll, tl)
+    assert_parity(per_utt, T(g["per_utt_loss"]), what="bf16->fp32 per-utterance loss")
+
+
+# --------------------------------------------------------------------------------------------
+# seeded synthetic draws of the BASELINE configs against the live oracle
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg,B,scale", [("c1", 4, 1.0), ("c2", 64, 1.0), ("c2", 16, 5.0), ("c3", 256, 1.0),
+                                         ("c4", 32, 1.0), ("c5", 6, 1.0), ("c5", 3, 5.0)])
+def test_config_vs_oracle(e2e, cfg, B, scale):
+    _, T_, V, Lmin, Lmax, seed, dtype, full = oracle.CONFIGS[cfg]
+    x, tg, ll, tl = oracle.make_inputs(B, T_, V, Lmin, Lmax, seed, dtype=dtype, full_length=full, scale=scale)
+    ref_leaf = x.float().clone().requires_grad_()
+    ref_loss = oracle.ctc_loss_module(oracle.engine(0), ref_leaf, tg, ll, tl, reduce=True, size_average=True)
+    ref_loss.backward()
+    leaf = x.cuda().requires_grad_()
+    loss = e2e.CTCLoss(reduce=True, size_average=True, after_logsoftmax=False)(leaf, *cuda(tg, ll, tl))
+    loss.backward()
+    rtol = BF16_RTOL if dtype == torch.bfloat16 else RTOL
+    assert_parity(loss, ref_loss, rtol=rtol, what=cfg + " loss")
+    assert_parity(leaf.grad, ref_leaf.grad, rtol=rtol, what=cfg + " grad")
+    # per-utterance losses and the engine contract (log-prob input, padding rows = exp(lp))
+    lp = torch.log_softmax(x.float(), 2)
+    l_ref, g_ref = oracle.engine(0).compute(lp, tg, ll, tl)
+    l_gpu, g_gpu = e2e.CTCLossEngine(0).compute(lp.cuda(), *cuda(tg, ll, tl))
+    assert_parity(l_gpu, l_ref, what=cfg + " engine losses")
+    assert_parity(g_gpu, g_ref, what=cfg + " engine grads")
+
+
+def test_every_lattice_shape_vs_oracle(e2e):
+    """Target lengths 0..70 (1..141 lattice cells) so every lane/warp-edge placement of the entry and
+    exit cells is hit for each cells-per-lane variant, with repeats and short T."""
+    g = torch.Generator().manual_seed(7)
+    B, T_, V = 71, 90, 7
+    x = torch.randn(B, T_, V, generator=g)
+    tl = torch.arange(B)
+    tg = torch.randint(1, V, (B, 70), generator=g)
+    tg[::3, 1::2] = tg[::3, 0:-1:2]                       # plenty of adjacent repeats
+    ll = torch.randint(T_ // 2, T_ + 1, (B,), generator=g)
+    lp = torch.log_softmax(x, 2)
+    l_ref, g_ref = oracle.engine(0).compute(lp, tg, ll, tl)
+    for K in ("2", "4", "8"):
+        os.environ["E2E_CTC_CELLS_PER_LANE"] = K
+        try:
+            l_gpu, g_gpu = e2e.CTCLossEngine(0).compute(lp.cuda(), *cuda(tg, ll, tl))
+        finally:
+            del os.environ["E2E_CTC_CELLS_PER_LANE"]
+        assert_parity(l_gpu, l_ref, what="K=%s losses" % K)
+        assert_parity(g_gpu, g_ref, what="K=%s grads" % K)
+
+
+def test_time_major_in_place_and_reduce_modes(e2e):
+    x, tg, ll, tl = oracle.make_inputs(6, 40, 12, 3, 9, 5)
+    x_tm = x.permute(1, 0, 2).contiguous()
+    for kw in (dict(), dict(reduce=True), dict(reduce=True, size_average=True), dict(size_average=True)):
+        ref_leaf = x_tm.clone().requires_grad_()
+        ref = oracle.ctc_loss_module(oracle.engine(0), ref_leaf, tg, ll, tl, time_major=True, **kw)
+        (ref.sum() if ref.dim() else ref).backward()
+        leaf = x_tm.cuda().requires_grad_()
+        out = e2e.CTCLoss(time_major=True, **kw)(leaf, *cuda(tg, ll, tl))
+        (out.sum() if out.dim() else out).backward()
+        assert out.shape == ref.shape                                    # [B] or 0-dim, never (1,)
+        assert_parity(out, ref, what="tm loss %s" % kw)
+        assert_parity(leaf.grad, ref_leaf.grad, what="tm grad %s" % kw)
+        assert leaf.grad.shape == x_tm.shape and leaf.grad.is_contiguous()
+
+
+def test_upstream_gradient_scaling_and_nan_through_zero(e2e):
+    x, tg, ll, tl = oracle.make_inputs(5, 12, 6, 2, 5, 9)
+    tg[1, :3] = 2
+    tl[1], ll[1] = 3, 3                                                   # infeasible: needs 5 frames
+    w = torch.tensor([0.5, 0.0, -2.0, 3.0, 1.0])
+    ref_leaf = x.clone().requires_grad_()
+    (oracle.ctc_loss_module(oracle.engine(0), ref_leaf, tg, ll, tl)[[0, 2, 3, 4]] * w[[0, 2, 3, 4]]).sum().backward()
+    leaf = x.cuda().requires_grad_()
+    loss = e2e.CTCLoss()(leaf, *cuda(tg, ll, tl))
+    assert torch.isposinf(loss[1])
+    loss.backward(w.cuda())                                               # zero upstream grad on the inf utterance
+    assert torch.isnan(leaf.grad[1]).all()                                # NaN survives * 0, as in the reference
+    keep = [0, 2, 3, 4]
+    assert_parity(leaf.grad[keep], ref_leaf.grad[keep], what="weighted grad")
+
+
+def test_non_contiguous_views_and_int32(e2e):
+    x, tg, ll, tl = oracle.make_inputs(4, 30, 10, 2, 8, 13)
+    big = torch.zeros(4, 30, 16)
+    big[:, :, 3:13] = x
+    view = big.cuda()[:, :, 3:13]                                        # unit alphabet stride, padded rows
+    lp_ref = torch.log_softmax(x, 2)
+    l_ref, g_ref = oracle.engine(0).compute(lp_ref, tg, ll, tl)
+    lp_view = torch.log_softmax(view, 2)
+    big_lp = torch.zeros(4, 30, 16, device="cuda")
+    big_lp[:, :, 3:13] = lp_view
+    l, g_ = e2e.CTCLossEngine(0).compute(big_lp[:, :, 3:13], tg.int().cuda(), ll.int().cuda(), tl.int().cuda())
+    assert_parity(l, l_ref, what="view losses")
+    assert_parity(g_, g_ref, what="view grads")
+    l2, g2 = e2e.CTCLossEngine(0).compute(lp_ref.cuda().transpose(1, 2).contiguous().transpose(1, 2),
+                                          *cuda(tg, ll, tl))              # alphabet stride != 1 -> repacked
+    assert_parity(g2, g_ref, what="repacked grads")
+
+
+def test_invalid_arguments_rejected(e2e):
+    x, tg, ll, tl = oracle.make_inputs(3, 10, 5, 1, 3, 1)
+    crit = e2e.CTCLoss()
+    with pytest.raises(ValueError):
+        crit(x.cuda(), tg, torch.tensor([10, 0, 10]), tl)               # T_i = 0
+    with pytest.raises(ValueError):
+        crit(x.cuda(), tg, torch.tensor([10, 11, 10]), tl)              # T_i > T
+    with pytest.raises(ValueError):
+        crit(x.cuda(), tg, ll, torch.tensor([1, 4, 1]))                 # L_i > Lmax
+    with pytest.raises(ValueError):
+        crit(x.cuda(), torch.full_like(tg, 5), ll, tl)                  # label >= V
+    with pytest.raises(ValueError):
+        e2e.CTCLoss(blank_idx=5)(x.cuda(), tg, ll, tl)                  # blank outside the alphabet
+    # device-resident lengths are checked on the device: flagged, NaN results, no crash
+    eng = e2e.CTCLossEngine(0)
+    losses, state = eng.forward(x.cuda(), tg.cuda(), torch.tensor([10, 0, 10]).cuda(), tl.cuda(), True)
+    assert eng.check(state) & 1
+    assert torch.isnan(losses[1]) and torch.isfinite(losses[[0, 2]]).all()
+
+
+# --------------------------------------------------------------------------------------------
+# greedy decoder: bit-exact
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["simple", "sm", "probs_1", "probs_2"])
+def test_greedy_known_answers(e2e, name):
+    g = gold("kat_greedy")
+    ll = g[name + "_ll"]
+    lengths = None if ll[0] < 0 else T(ll)
+    dec = e2e.CTCDecoder(beam_width=1, blank_idx=int(g[name + "_blank"]), labels=[str(s) for s in g[name + "_labels"]],
+                         time_major=False)
+    for dev in ("cpu", "cuda"):
+        r = dec.decode(T(g[name + "_x"]).to(dev), lengths)
+        assert r.decoded_sentences == [str(s) for s in g[name + "_sentences"]]
+        assert r.decoded_targets.dtype == torch.int64 and not r.decoded_targets.is_cuda
+        assert torch.equal(r.decoded_targets, T(g[name + "_targets"]))
+        assert torch.equal(r.decoded_targets_lengths, T(g[name + "_lengths"]))
+        r2 = dec.decode_greedy(T(g[name + "_x"]).to(dev), lengths)
+        assert torch.equal(r2.decoded_targets, r.decoded_targets)
+
+
+def test_greedy_ties_nan_bf16_time_major(e2e):
+    g = gold("greedy_random")
+    x, ll, blank = T(g["x"]), T(g["ll"]), int(g["blank"])
+    dec = e2e.CTCDecoder(beam_width=1, blank_idx=blank)
+    for dev in ("cpu", "cuda"):
+        r = dec.decode(x.to(dev), ll.to(dev))
+        assert torch.equal(r.decoded_targets, T(g["targets"])) and torch.equal(r.decoded_targets_lengths, T(g["lengths"]))
+        r = dec.decode(x.to(dev))                                         # lengths None -> all frames
+        assert torch.equal(r.decoded_targets, T(g["targets_full"])) and torch.equal(r.decoded_targets_lengths, T(g["lengths_full"]))
+        assert r.decoded_sentences == [""] * x.size(0)
+    xb = T(g["xb_bits"]).view(torch.bfloat16)
+    for dev in ("cpu", "cuda"):
+        r = e2e.CTCDecoder(beam_width=1).decode(xb.to(dev), T(g["llb"]))
+        assert torch.equal(r.decoded_targets, T(g["targets_b"])) and torch.equal(r.decoded_targets_lengths, T(g["lengths_b"]))
+        r = e2e.CTCDecoder(beam_width=1, time_major=True).decode(xb.transpose(0, 1).contiguous().to(dev), T(g["llb"]))
+        assert torch.equal(r.decoded_targets, T(g["targets_b"]))
+        r = e2e.CTCDecoder(beam_width=1, time_major=True).decode(xb.to(dev).transpose(0, 1), T(g["llb"]))  # strided view
+        assert torch.equal(r.decoded_targets, T(g["targets_b"]))
+
+
+def test_greedy_c4_full_size_vs_oracle(e2e):
+    B, T_, V, Lmin, Lmax, seed, _, _ = oracle.CONFIGS["c4"]
+    x, _, ll, _ = oracle.make_inputs(B, T_, V, Lmin, Lmax, seed)
+    ref = oracle.greedy_decode(x, ll)
+    r = e2e.CTCDecoder(beam_width=1).decode(x.cuda(), ll.cuda())
+    assert torch.equal(r.decoded_targets, ref[0]) and torch.equal(r.decoded_targets_lengths, ref[1])
+    r16 = e2e.CTCDecoder(beam_width=1).decode(x.half().cuda(), ll)
+    ref16 = oracle.greedy_decode(x.half(), ll)
+    assert torch.equal(r16.decoded_targets, ref16[0])
+    with pytest.raises(NotImplementedError):
+        e2e.CTCDecoder(beam_width=20).decode(x.cuda())
+
+
+# --------------------------------------------------------------------------------------------
+# BASELINE full sizes: size-independent properties
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg,B", [("c3", 1024), ("c4", 128), ("c5", 96)])
+def test_full_size_properties(e2e, cfg, B):
+    _, T_, V, Lmin, Lmax, seed, dtype, full = oracle.CONFIGS[cfg]
+    x, tg, ll, tl = oracle.make_inputs(B, T_, V, Lmin, Lmax, seed, dtype=torch.float32, full_length=full)
+    leaf = x.cuda().requires_grad_()
+    tgc, llc, tlc = cuda(tg, ll, tl)
+    per_utt = e2e.CTCLoss()(leaf, tgc, llc, tlc)
+    per_utt.sum().backward()
+    grad = leaf.grad
+    assert torch.isfinite(per_utt).all() and torch.isfinite(grad).all()
+    valid = (torch.arange(T_, device="cuda")[None, :] < llc[:, None])
+    # (1) softmax and posterior both sum to one over the alphabet: gradient rows sum to ~0
+    assert float(grad.sum(2).abs().max()) < 2e-4
+    # (2) padding frames get exactly zero (fused log-softmax backward), valid frames do not
+    assert float(grad[~valid].abs().max()) == 0.0
+    # (3) blank posterior mass: d loss / d logit[blank] = softmax - posterior, bounded by 1 in magnitude
+    assert float(grad.abs().max()) <= 1.0 + 1e-5
+    # (4) the reduced losses are the sum / mean of the per-utterance losses
+    s = e2e.CTCLoss(reduce=True)(x.cuda(), tgc, llc, tlc)
+    m = e2e.CTCLoss(reduce=True, size_average=True)(x.cuda(), tgc, llc, tlc)
+    assert abs(s.item() - per_utt.double().sum().item()) <= 1e-6 * abs(s.item())
+    assert abs(m.item() - per_utt.double().mean().item()) <= 1e-6 * abs(m.item())
+    # (5) the loss of an utterance does not depend on its batch neighbours or on padding frames
+    idx = torch.tensor([0, B // 2, B - 1])
+    sub = e2e.CTCLoss()(x[idx].cuda(), tg[idx].cuda(), ll[idx].cuda(), tl[idx].cuda())
+    assert torch.equal(sub, per_utt[idx.cuda()])
+    # (6) spot check against the oracle
+    lp = torch.log_softmax(x[idx], 2)
+    l_ref, _ = oracle.engine(0).compute(lp, tg[idx], ll[idx], tl[idx])
+    assert_parity(sub, l_ref, what=cfg + " spot losses")
+
+
+def test_greedy_idempotence_full_size(e2e):
+    """Decoding the one-hot re-encoding of a collapsed greedy path returns the same labels."""
+    B, T_, V, *_ = oracle.CONFIGS["c3"]
+    x = torch.randn(B, T_, V, generator=torch.Generator().manual_seed(2)).cuda()
+    dec = e2e.CTCDecoder(beam_width=1)
+    r = dec.decode(x)
+    onehot = torch.zeros(B, T_, V, device="cuda")
+    onehot[:, :, 0] = 0.5                                                 # blank wins wherever nothing is set
+    tgt = r.decoded_targets.cuda()
+    pos = torch.arange(T_, device="cuda")[None, :].expand(B, T_)
+    mask = pos < r.decoded_targets_lengths.cuda()[:, None]
+    # place label i at frame 2i (blank between) when it fits, else skip the check for that row
+    fits = r.decoded_targets_lengths * 2 <= T_
+    rows = torch.nonzero(fits.cuda()).flatten()
+    for b in rows[:64].tolist():
+        n = int(r.decoded_targets_lengths[b])
+        onehot[b, torch.arange(n, device="cuda") * 2, tgt[b, :n]] = 1.0
+    r2 = dec.decode(onehot)
+    for b in rows[:64].tolist():
+        n = int(r.decoded_targets_lengths[b])
+        assert int(r2.decoded_targets_lengths[b]) == n
+        assert torch.equal(r2.decoded_targets[b, :n], r.decoded_targets[b, :n])
+    assert bool(mask.any())
+
+
+# --------------------------------------------------------------------------------------------
+# the raw C ABI (what a non-Python host binds)
+# --------------------------------------------------------------------------------------------
+def test_c_abi_direct_calls(e2e):
+    from end2end_b200 import _lib
+    L = _lib.load()
+    x, tg, ll, tl = oracle.make_inputs(4, 50, 28, 10, 29, 0, full_length=True)
+    lp = torch.log_softmax(x, 2).cuda()
+    tgc, llc, tlc = cuda(tg, ll, tl)
+    d = _lib.Desc()
+    d.batch, d.max_frames, d.alphabet, d.max_targets = 4, 50, 28, 29
+    d.blank_idx, d.dtype, d.targets_itype, d.lengths_itype, d.from_logits = 0, _lib.E2E_F32, _lib.E2E_I64, _lib.E2E_I64, 0
+    d.logits_stride_b, d.logits_stride_t = 50 * 28, 28
+    d.grads_stride_b, d.grads_stride_t = 50 * 28, 28
+    d.targets_stride_b = 29
+    n = L.e2e_ctc_loss_workspace_bytes(ctypes.byref(d))
+    assert n > 0
+    ws = torch.empty(n, dtype=torch.uint8, device="cuda")
+    losses = torch.empty(4, device="cuda")
+    grads = torch.empty_like(lp)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    before = _lib.launch_count()
+    rc = L.e2e_ctc_loss_fwd_bwd_device(ctypes.byref(d), p(lp), p(tgc), p(llc), p(tlc), p(losses), p(grads), p(ws), n, stream)
+    assert rc == 0, L.e2e_last_error_string()
+    assert _lib.launch_count() - before == 3                                # row stats, lattice, gradient
+    l_ref, g_ref = oracle.engine(0).compute(lp.cpu(), tg, ll, tl)
+    assert_parity(losses, l_ref, what="abi losses")
+    assert_parity(grads, g_ref, what="abi grads")
+    total = torch.empty((), device="cuda")
+    pair = torch.empty(2, dtype=torch.float64, device="cuda")
+    assert L.e2e_ctc_loss_reduce_device(p(losses), _lib.E2E_F32, 4, 0.25, p(total), p(pair), stream) == 0
+    assert abs(total.item() - l_ref.double().mean().item()) < 1e-4 and pair[1].item() == 4.0
+    # error paths: small / misaligned workspace, null pointers, bad descriptor
+    assert L.e2e_ctc_loss_fwd_bwd_device(ctypes.byref(d), p(lp), p(tgc), p(llc), p(tlc), p(losses), p(grads), p(ws), n - 1, stream) == 3
+    assert L.e2e_ctc_loss_fwd_bwd_device(ctypes.byref(d), p(lp), p(tgc), p(llc), p(tlc), p(losses), p(grads),
+                                         ctypes.c_void_p(ws.data_ptr() + 8), n, stream) == 3
+    assert L.e2e_ctc_loss_fwd_bwd_device(ctypes.byref(d), None, p(tgc), p(llc), p(tlc), p(losses), p(grads), p(ws), n, stream) == 1
+    assert b"null" in L.e2e_last_error_string()
+    d.blank_idx = 28
+    assert L.e2e_ctc_loss_workspace_bytes(ctypes.byref(d)) == 0
+    torch.cuda.synchronize()
+
+
+def test_host_engine_traffic_and_pinned_buffers(e2e):
+    x, tg, ll, tl = oracle.make_inputs(8, 60, 29, 5, 20, 17)
+    eng = e2e.CTCLossEngine(0)
+    lp = torch.log_softmax(x, 2).pin_memory()
+    losses, grads = eng.compute(lp, tg, ll, tl)
+    h2d, d2h = eng.last_host_traffic()
+    assert h2d == lp.numel() * 4 + tg.numel() * 8 + 2 * 8 * 8 and d2h == lp.numel() * 4 + 8 * 4
+    l_ref, g_ref = oracle.engine(0).compute(lp, tg, ll, tl)
+    assert_parity(losses, l_ref, what="host losses")
+    assert_parity(grads, g_ref, what="host grads")
+    # the module on CPU tensors takes the same route (forward) and scales on the host (backward)
+    leaf = x.clone().requires_grad_()
+    loss = e2e.CTCLoss(reduce=True, size_average=True)(leaf, tg, ll, tl)
+    loss.backward()
+    ref_leaf = x.clone().requires_grad_()
+    oracle.ctc_loss_module(oracle.engine(0), ref_leaf, tg, ll, tl, reduce=True, size_average=True).backward()
+    assert_parity(leaf.grad, ref_leaf.grad, what="host module grad")
