@@ -106,17 +106,25 @@ bool make_loss_plan(const e2e_ctc_desc& d, LossPlan* p) {
   const int NW = ((S + K - 1) / K + 31) / 32;
   if (NW > kMaxLatticeWarps) return false;
   p->K = K; p->NW = NW; p->cells = 32 * K * NW; p->lanes = 32 * NW;
-  p->lstride = (d.max_targets + 2 + 1) & ~1;
-  int ring = env_int("E2E_CTC_RING", 16);
-  if (ring != 4 && ring != 8 && ring != 16 && ring != 32) ring = 16;
-  auto smem_of = [&](int r) {
-    return (size_t)r * p->lstride * 8 + 64 * 32 + 33 * 8 + 16 * 8 + 36 * 4 + (size_t)d.max_targets * 4 + 64;
+  // emission staging: by symbol when the alphabet is no larger than the label row, else by label
+  p->dense = d.alphabet <= d.max_targets + 1;
+  p->rowlen = p->dense ? d.alphabet : d.max_targets + 1;
+  p->lstride = (p->rowlen + 1 + 1) & ~1;
+  const size_t slot = d.dtype == E2E_F64 ? 32 : 16;
+  auto smem_of = [&](int cs) {
+    const size_t ring = (size_t)4 << cs;
+    return ring * p->lstride * 8 + ring * p->rowlen * slot + 64 * 32 + 33 * 8 + 16 * 8 + 36 * 4 +
+           (size_t)d.max_targets * 4 + 64;
   };
-  while (ring > 4 && smem_of(ring) > 160 * 1024) ring >>= 1;
-  if (smem_of(ring) > 220 * 1024) return false;
-  p->ring = ring;
-  p->chunk = ring / 4;
-  p->smem = smem_of(ring);
+  int cs = env_int("E2E_CTC_CHUNK_LOG2", -1);
+  if (cs < 0 || cs > 3) {  // aim at ~256 staged items per hand-off
+    cs = 3;
+    while (cs > 0 && (p->rowlen << cs) > 256) --cs;
+  }
+  while (cs > 0 && smem_of(cs) > 160 * 1024) --cs;
+  if (smem_of(cs) > 220 * 1024) return false;
+  p->chunk_log2 = cs;
+  p->smem = smem_of(cs);
   const size_t rows = (size_t)d.batch * d.max_frames;
   size_t off = 0;
   p->off_status = off; off += 256;

@@ -16,9 +16,10 @@ struct LossPlan {
   int NW;           // lattice warps per CTA
   int cells;        // 32*K*NW  >= 2*Lmax+1   (row stride of post / hv)
   int lanes;        // 32*NW                  (row stride of he)
-  int ring;         // emission ring depth in frames
-  int chunk;        // frames per producer hand-off
-  int lstride;      // doubles per ring frame (Lmax+2 rounded up to even)
+  int dense;        // emission ring indexed by symbol (V <= Lmax+1) instead of by label position
+  int rowlen;       // emissions staged per frame: V (dense) or Lmax+1 (gather)
+  int chunk_log2;   // frames per producer hand-off = 1 << chunk_log2; the ring holds 4 chunks
+  int lstride;      // doubles per ring frame (rowlen + zero slot, rounded up to even)
   size_t smem;      // dynamic shared memory of the lattice kernel
   // byte offsets into the workspace
   size_t off_status, off_flags, off_stats, off_hv, off_he, off_post, total;

@@ -39,8 +39,10 @@ struct LatticeParams {
   void* losses;
   int* status; int* flags;
   uint32_t* hv; int* he; float* post;
-  int cells, lanes, ring, chunk, lstride;
+  int cells, lanes, chunk_log2, lstride, dense, rowlen_max;
 };
+
+constexpr int kNumChunks = 4;   // E-ring / cp.async pipeline depth, in chunks of 2^chunk_log2 frames
 
 struct __align__(16) Boundary {
   double x0, x1;
@@ -157,48 +159,106 @@ __device__ __forceinline__ double emission_f32(float x, float m, float ls, int f
 }
 __device__ __forceinline__ double emission_f64(double x, double m, double ls) { return exp((x - m) - ls); }
 
-template <bool BWD>
-__device__ void run_producer(const LatticeParams& p, int b, int Ti, int Li, const int* s_lab,
-                             double* s_E, uint64_t* s_full, uint64_t* s_empty, double* s_lsesum,
+// cp.async (LDGSTS) of 4 / 8 / 16 bytes, global -> this CTA's shared memory, no register staging
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "n"(BYTES)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Producer warps: stage the emissions of `chunk` frames at a time into the E ring.
+//   dense  mode (V <= Lmax+1): E[f][v]   = p(t_f, v)        for every symbol v      (rowlen = V)
+//   gather mode              : E[f][0]   = p(t_f, blank), E[f][1+i] = p(t_f, label_i) (rowlen = L_i+1)
+// Every item (raw logit + its row's {max, logsumexp}) is fetched with cp.async into a slot that
+// only the issuing thread reads back, kNumChunks chunks ahead of its conversion, so the L2 latency
+// of the gathers never reaches the lattice warps; conversion = one expf per item.
+template <bool BWD, bool F64>
+__device__ void run_producer(const LatticeParams& p, int b, int Ti, int Li, const int* s_lab, double* s_E,
+                             unsigned char* s_raw, uint64_t* s_full, uint64_t* s_empty, double* s_lsesum,
                              int ptid, int npt) {
-  const int nch = p.ring / p.chunk;
-  const int L1 = Li + 1;
-  double lsesum = 0.0;
-  int c = 0;
-  for (int i0 = 0; i0 < Ti; i0 += p.chunk, ++c) {
-    const int slot_c = c % nch;
-    mbar_wait(&s_empty[slot_c], ((c / nch) & 1) ^ 1);
-    const int nf = min(p.chunk, Ti - i0);
-    for (int f = 0; f < nf; ++f) {
-      const int i = i0 + f;
-      const int t = BWD ? (Ti - 1 - i) : i;
-      const long long row = (long long)b * p.T + t;
-      const long long base = (long long)b * p.sb + (long long)t * p.st;
-      double* Erow = s_E + (size_t)(slot_c * p.chunk + f) * p.lstride;
-      if (p.dtype == E2E_F64) {
-        const double m = __ldg(reinterpret_cast<const double*>(p.stats) + 2 * row);
-        const double ls = __ldg(reinterpret_cast<const double*>(p.stats) + 2 * row + 1);
-        for (int k = ptid; k < L1; k += npt) {
-          const int v = (k == 0) ? p.blank : s_lab[k - 1];
-          const double x = __ldg(reinterpret_cast<const double*>(p.logits) + base + v);
-          Erow[k] = emission_f64(x, m, ls);
+  constexpr int SLOT = F64 ? 32 : 16;          // {raw, max, logsumexp} per item
+  const int cs = p.chunk_log2, CF = 1 << cs;
+  const int rowlen = p.dense ? p.V : Li + 1;
+  const int nchunks = (Ti + CF - 1) >> cs;
+  const int slots_per_chunk = CF * p.rowlen_max;
+  const size_t esz = p.dtype == E2E_F32 ? 4 : (p.dtype == E2E_F64 ? 8 : 2);
+  const char* lbase = reinterpret_cast<const char*>(p.logits);
+
+  auto symbol = [&](int k) { return p.dense ? k : (k == 0 ? p.blank : s_lab[k - 1]); };
+  auto issue = [&](int c) {
+    if (c < nchunks) {
+      const int nf = min(CF, Ti - (c << cs));
+      unsigned char* chunk_raw = s_raw + (size_t)(c & (kNumChunks - 1)) * slots_per_chunk * SLOT;
+      for (int it = ptid; it < nf * rowlen; it += npt) {
+        const int f = it / rowlen, k = it - f * rowlen;
+        const int i = (c << cs) + f;
+        const int t = BWD ? (Ti - 1 - i) : i;
+        const long long row = (long long)b * p.T + t;
+        const long long e = (long long)b * p.sb + (long long)t * p.st + symbol(k);
+        unsigned char* slot = chunk_raw + (size_t)it * SLOT;
+        if (F64) {
+          cp_async<8>(slot, lbase + e * 8);
+          cp_async<16>(slot + 16, reinterpret_cast<const char*>(p.stats) + row * 16);
+        } else {
+          // 16-bit elements: fetch the aligned 32-bit word that holds the element
+          const char* src = lbase + e * esz;
+          cp_async<4>(slot, reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3));
+          cp_async<8>(slot + 8, reinterpret_cast<const char*>(p.stats) + row * 8);
         }
-        if (!BWD && ptid == 0) lsesum += m + ls;
-      } else {
-        const float m = __ldg(reinterpret_cast<const float*>(p.stats) + 2 * row);
-        const float ls = __ldg(reinterpret_cast<const float*>(p.stats) + 2 * row + 1);
-        for (int k = ptid; k < L1; k += npt) {
-          const int v = (k == 0) ? p.blank : s_lab[k - 1];
-          const float x = load_as_float(p.logits, p.dtype, base + v);
-          Erow[k] = emission_f32(x, m, ls, p.from_logits);
-        }
-        if (!BWD && ptid == 0) lsesum += (double)m + (double)ls;
       }
     }
-    // the row-normaliser sum rides on the last hand-off (release/acquire through the mbarrier)
-    if (!BWD && ptid == 0 && i0 + p.chunk >= Ti) *s_lsesum = lsesum;
+    cp_async_commit();   // one group per chunk, also when empty, so the wait depth stays uniform
+  };
+
+  for (int c = 0; c < kNumChunks; ++c) issue(c);
+  double lsesum = 0.0;
+  for (int c = 0; c < nchunks; ++c) {
+    const int slot_c = c & (kNumChunks - 1);
+    cp_async_wait<kNumChunks - 1>();                       // this thread's copies of chunk c have landed
+    mbar_wait(&s_empty[slot_c], ((c / kNumChunks) & 1) ^ 1);  // the lattice warps released the E slot
+    const int nf = min(CF, Ti - (c << cs));
+    const unsigned char* chunk_raw = s_raw + (size_t)slot_c * slots_per_chunk * SLOT;
+    for (int it = ptid; it < nf * rowlen; it += npt) {
+      const int f = it / rowlen, k = it - f * rowlen;
+      const unsigned char* slot = chunk_raw + (size_t)it * SLOT;
+      double em;
+      if (F64) {
+        const double x = *reinterpret_cast<const double*>(slot);
+        const double2 st = *reinterpret_cast<const double2*>(slot + 16);
+        em = emission_f64(x, st.x, st.y);
+      } else {
+        const uint32_t raw = *reinterpret_cast<const uint32_t*>(slot);
+        const float2 st = *reinterpret_cast<const float2*>(slot + 8);
+        float x;
+        if (p.dtype == E2E_F32) {
+          x = __uint_as_float(raw);
+        } else {
+          const int i = (c << cs) + f;
+          const int t = BWD ? (Ti - 1 - i) : i;
+          const long long e = (long long)b * p.sb + (long long)t * p.st + symbol(k);
+          const uint32_t half = ((reinterpret_cast<uintptr_t>(lbase) + (uintptr_t)(e * 2)) & 2) ? (raw >> 16) : (raw & 0xffffu);
+          x = p.dtype == E2E_BF16 ? __uint_as_float(half << 16) : __half2float(__ushort_as_half((unsigned short)half));
+        }
+        em = emission_f32(x, st.x, st.y, p.from_logits);
+      }
+      s_E[(size_t)((slot_c << cs) + f) * p.lstride + k] = em;
+    }
+    if (!BWD && !p.from_logits && ptid == 0) {
+      // sum of the row normalisers (log-prob input only), fixed order => deterministic loss
+      for (int f = 0; f < nf; ++f) {
+        const long long row = (long long)b * p.T + ((c << cs) + f);
+        if (F64) lsesum += __ldg(reinterpret_cast<const double*>(p.stats) + 2 * row) + __ldg(reinterpret_cast<const double*>(p.stats) + 2 * row + 1);
+        else lsesum += (double)__ldg(reinterpret_cast<const float*>(p.stats) + 2 * row) + (double)__ldg(reinterpret_cast<const float*>(p.stats) + 2 * row + 1);
+      }
+      if (c == nchunks - 1) *s_lsesum = lsesum;     // rides on the last hand-off (mbarrier release/acquire)
+    }
     mbar_arrive(&s_full[slot_c]);
+    issue(c + kNumChunks);
   }
+  cp_async_wait<0>();
 }
 
 // ---- block-wide sum of per-lane values v * 2^ex over the Wi lattice warps ---------------------
@@ -225,13 +285,13 @@ __device__ __forceinline__ void block_sum_scaled(double v, int ex, double* s_red
 // ---- one lattice frame for one lane -----------------------------------------------------------
 template <int K, bool BWD>
 __device__ __forceinline__ void lattice_step(double (&x)[K], int& e, int& sh, const double* Erow,
-                                             const int (&eidx)[K / 2], unsigned bvalid, unsigned skipm,
+                                             const int (&eidx)[K / 2], int bidx, unsigned bvalid, unsigned skipm,
                                              const Boundary* bnd_rd, Boundary* bnd_wr, int w, int Wi,
                                              int lane, double (&val)[K], int& en_out) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int H = K / 2;
   // emissions for this frame
-  const double pb = Erow[0];
+  const double pb = Erow[bidx];
   double pl[H];
 #pragma unroll
   for (int h = 0; h < H; h++) pl[h] = Erow[eidx[h]];
@@ -314,9 +374,13 @@ __device__ void run_chain(const LatticeParams& p, int b, int Ti, int Li, const i
   const int lane_g = w * 32 + lane;
   const int s0 = lane_g * K;
   const bool lane_active = s0 < S;
-  const int nch = p.ring / p.chunk;
+  const int cs = p.chunk_log2;
+  const int ring_mask = (kNumChunks << cs) - 1, chunk_mask = (1 << cs) - 1;
   const int nthr = Wi * 32;
 
+  // emission ring columns: dense mode indexes by symbol, gather mode by label position
+  const int zero_slot = p.dense ? p.V : Li + 1;
+  const int bidx = p.dense ? p.blank : 0;
   int eidx[H];
   unsigned bvalid = 0, skipm = 0;
 #pragma unroll
@@ -324,7 +388,7 @@ __device__ void run_chain(const LatticeParams& p, int b, int Ti, int Li, const i
     const int li = lane_g * H + h;  // label index of cell s0+2h+1
     if (s0 + 2 * h < S) bvalid |= 1u << h;
     const bool lv = li < Li;
-    eidx[h] = lv ? 1 + li : Li + 1;  // Li+1 is the ring's zero slot
+    eidx[h] = lv ? (p.dense ? s_lab[li] : 1 + li) : zero_slot;
     if (lv) {
       const int lab = s_lab[li];
       bool sk;
@@ -365,13 +429,13 @@ __device__ void run_chain(const LatticeParams& p, int b, int Ti, int Li, const i
   // ---------------- first half: sweep and store ----------------
   for (; i < nstore; ++i) {
     const int t = BWD ? (Ti - 1 - i) : i;
-    if (i % p.chunk == 0) mbar_wait(&s_full[(i / p.chunk) % nch], ((i / p.chunk) / nch) & 1);
+    if ((i & chunk_mask) == 0) mbar_wait(&s_full[(i >> cs) & (kNumChunks - 1)], ((i >> cs) / kNumChunks) & 1);
     if (Wi > 1) chain_barrier(nthr);
-    lattice_step<K, BWD>(x, e, sh, s_E + (size_t)(i % p.ring) * p.lstride, eidx, bvalid, skipm,
+    lattice_step<K, BWD>(x, e, sh, s_E + (size_t)(i & ring_mask) * p.lstride, eidx, bidx, bvalid, skipm,
                          s_bnd + (i & 1) * 32, s_bnd + ((i + 1) & 1) * 32, w, Wi, lane, val, en);
-    if ((i + 1) % p.chunk == 0 || i + 1 == Ti) {
+    if (((i + 1) & chunk_mask) == 0 || i + 1 == Ti) {
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[(i / p.chunk) % nch]);
+      if (lane == 0) mbar_arrive(&s_empty[(i >> cs) & (kNumChunks - 1)]);
     }
     if (lane_active) {
       uint32_t pk[K];
@@ -397,13 +461,13 @@ __device__ void run_chain(const LatticeParams& p, int b, int Ti, int Li, const i
   int Ez;
   {
     const int t = BWD ? (Ti - 1 - i) : i;
-    if (i % p.chunk == 0) mbar_wait(&s_full[(i / p.chunk) % nch], ((i / p.chunk) / nch) & 1);
+    if ((i & chunk_mask) == 0) mbar_wait(&s_full[(i >> cs) & (kNumChunks - 1)], ((i >> cs) / kNumChunks) & 1);
     if (Wi > 1) chain_barrier(nthr);
-    lattice_step<K, BWD>(x, e, sh, s_E + (size_t)(i % p.ring) * p.lstride, eidx, bvalid, skipm,
+    lattice_step<K, BWD>(x, e, sh, s_E + (size_t)(i & ring_mask) * p.lstride, eidx, bidx, bvalid, skipm,
                          s_bnd + (i & 1) * 32, s_bnd + ((i + 1) & 1) * 32, w, Wi, lane, val, en);
-    if ((i + 1) % p.chunk == 0 || i + 1 == Ti) {
+    if (((i + 1) & chunk_mask) == 0 || i + 1 == Ti) {
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[(i / p.chunk) % nch]);
+      if (lane == 0) mbar_arrive(&s_empty[(i >> cs) & (kNumChunks - 1)]);
     }
     uint32_t ov[K];
     int oe = kNegExp;
@@ -450,13 +514,13 @@ __device__ void run_chain(const LatticeParams& p, int b, int Ti, int Li, const i
       const int iu = i + u;
       if (iu < Ti) {
         const int t = BWD ? (Ti - 1 - iu) : iu;
-        if (iu % p.chunk == 0) mbar_wait(&s_full[(iu / p.chunk) % nch], ((iu / p.chunk) / nch) & 1);
+        if ((iu & chunk_mask) == 0) mbar_wait(&s_full[(iu >> cs) & (kNumChunks - 1)], ((iu >> cs) / kNumChunks) & 1);
         if (Wi > 1) chain_barrier(nthr);
-        lattice_step<K, BWD>(x, e, sh, s_E + (size_t)(iu % p.ring) * p.lstride, eidx, bvalid, skipm,
+        lattice_step<K, BWD>(x, e, sh, s_E + (size_t)(iu & ring_mask) * p.lstride, eidx, bidx, bvalid, skipm,
                              s_bnd + (iu & 1) * 32, s_bnd + ((iu + 1) & 1) * 32, w, Wi, lane, val, en);
-        if ((iu + 1) % p.chunk == 0 || iu + 1 == Ti) {
+        if (((iu + 1) & chunk_mask) == 0 || iu + 1 == Ti) {
           __syncwarp();
-          if (lane == 0) mbar_arrive(&s_empty[(iu / p.chunk) % nch]);
+          if (lane == 0) mbar_arrive(&s_empty[(iu >> cs) & (kNumChunks - 1)]);
         }
         if (lane_active) {
           const double c = pow2i(en + oeb[u] - Ez) * invz;
@@ -506,9 +570,10 @@ template <int K>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLatticeMaxThreads, 1)
 ctc_lattice_kernel(const LatticeParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nch = p.ring / p.chunk;
+  const int ring = kNumChunks << p.chunk_log2;
   double* s_E = reinterpret_cast<double*>(smem_raw);
-  Boundary* s_bnd = reinterpret_cast<Boundary*>(s_E + (size_t)p.ring * p.lstride);
+  unsigned char* s_raw = reinterpret_cast<unsigned char*>(s_E + (size_t)ring * p.lstride);
+  Boundary* s_bnd = reinterpret_cast<Boundary*>(s_raw + (size_t)ring * p.rowlen_max * (p.dtype == E2E_F64 ? 32 : 16));
   double* s_redd = reinterpret_cast<double*>(s_bnd + 64);
   double* s_lsesum = s_redd + 32;
   uint64_t* s_full = reinterpret_cast<uint64_t*>(s_lsesum + 1);
@@ -563,14 +628,14 @@ ctc_lattice_kernel(const LatticeParams p) {
   const int Wi = ((S + K - 1) / K + 31) / 32;
   if (tid == 0) {
     if (!bwd) p.flags[b] = 0;
-    for (int c = 0; c < nch; c++) {
+    for (int c = 0; c < kNumChunks; c++) {
       mbar_init(&s_full[c], kProducerWarps * 32);
       mbar_init(&s_empty[c], Wi);
     }
     mbar_init(s_meet, Wi);
     *s_lsesum = 0.0;
   }
-  for (int f = tid; f < p.ring; f += blockDim.x) s_E[(size_t)f * p.lstride + Li + 1] = 0.0;
+  for (int f = tid; f < ring; f += blockDim.x) s_E[(size_t)f * p.lstride + (p.dense ? p.V : Li + 1)] = 0.0;
   for (int q = tid; q < 64; q += blockDim.x) { s_bnd[q].x0 = 0.0; s_bnd[q].x1 = 0.0; s_bnd[q].e = kNegExp; }
   __syncthreads();
   // Both CTAs of the pair took the same early-exit decisions above, so both reach this point:
@@ -580,8 +645,14 @@ ctc_lattice_kernel(const LatticeParams p) {
 
   if (w >= NW) {  // emission producers
     const int ptid = tid - NW * 32;
-    if (bwd) run_producer<true>(p, b, Ti, Li, s_lab, s_E, s_full, s_empty, s_lsesum, ptid, kProducerWarps * 32);
-    else run_producer<false>(p, b, Ti, Li, s_lab, s_E, s_full, s_empty, s_lsesum, ptid, kProducerWarps * 32);
+    const int npt = kProducerWarps * 32;
+    if (p.dtype == E2E_F64) {
+      if (bwd) run_producer<true, true>(p, b, Ti, Li, s_lab, s_E, s_raw, s_full, s_empty, s_lsesum, ptid, npt);
+      else run_producer<false, true>(p, b, Ti, Li, s_lab, s_E, s_raw, s_full, s_empty, s_lsesum, ptid, npt);
+    } else {
+      if (bwd) run_producer<true, false>(p, b, Ti, Li, s_lab, s_E, s_raw, s_full, s_empty, s_lsesum, ptid, npt);
+      else run_producer<false, false>(p, b, Ti, Li, s_lab, s_E, s_raw, s_full, s_empty, s_lsesum, ptid, npt);
+    }
     return;
   }
   if (w >= Wi) return;
@@ -616,7 +687,8 @@ int launch_lattice(const e2e_ctc_desc& d, const LossPlan& p, const void* logits,
   lp.hv = reinterpret_cast<uint32_t*>(ws + p.off_hv);
   lp.he = reinterpret_cast<int*>(ws + p.off_he);
   lp.post = reinterpret_cast<float*>(ws + p.off_post);
-  lp.cells = p.cells; lp.lanes = p.lanes; lp.ring = p.ring; lp.chunk = p.chunk; lp.lstride = p.lstride;
+  lp.cells = p.cells; lp.lanes = p.lanes; lp.chunk_log2 = p.chunk_log2; lp.lstride = p.lstride;
+  lp.dense = p.dense; lp.rowlen_max = p.rowlen;
   switch (p.K) {
     case 2: return launch_k<2>(lp, p, s);
     case 4: return launch_k<4>(lp, p, s);

@@ -70,7 +70,7 @@ def test_reference_known_answers(e2e, name):
                        blank_idx=int(g[name + "_blank"]))
     costs = []
     for dev in ("cpu", "cuda"):                                        # host-tensor path and device path
-        leaf = lp_tm.to(dev).requires_grad_()
+        leaf = lp_tm.detach().clone().to(dev).requires_grad_()
         cost = crit(leaf, tg, ll, tl)                                   # int32 CPU targets/lengths, as in the reference
         cost.backward()
         costs.append(cost.item())
