@@ -17,13 +17,13 @@ E2E_I32, E2E_I64 = 0, 1
 EXPORTS = (
     "e2e_ctc_version", "e2e_last_error_string", "e2e_ctc_get_limits",
     "e2e_ctc_loss_workspace_bytes", "e2e_ctc_loss_forward_device", "e2e_ctc_loss_backward_device",
-    "e2e_ctc_loss_fwd_bwd_device", "e2e_ctc_loss_reduce_device", "e2e_ctc_loss_check_device",
+    "e2e_ctc_loss_fwd_bwd_device", "e2e_ctc_loss_step_device", "e2e_ctc_scale_rows_device", "e2e_ctc_loss_reduce_device", "e2e_ctc_loss_check_device",
     "e2e_ctc_greedy_workspace_bytes", "e2e_ctc_greedy_decode_device",
     "e2e_ctc_engine_create", "e2e_ctc_engine_destroy", "e2e_ctc_engine_loss_host",
     "e2e_ctc_engine_greedy_host", "e2e_ctc_engine_last_traffic", "e2e_ctc_launch_count",
     "e2e_ctc_profile_enable", "e2e_ctc_profile_read",
 )
-KERNEL_KINDS = ("row_stats", "lattice", "gradient", "loss_reduce", "argmax", "collapse")
+KERNEL_KINDS = ("row_stats", "lattice", "gradient", "loss_reduce", "argmax", "collapse", "scale_rows")
 
 
 class Desc(ctypes.Structure):
@@ -74,6 +74,8 @@ def load():
     L.e2e_ctc_loss_forward_device.argtypes = [dp, vp, vp, vp, vp, vp, vp, sz, vp]
     L.e2e_ctc_loss_backward_device.argtypes = [dp, vp, vp, vp, vp, vp, i32, dbl, vp, vp, sz, vp]
     L.e2e_ctc_loss_fwd_bwd_device.argtypes = [dp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.e2e_ctc_loss_step_device.argtypes = [dp, vp, vp, vp, vp, vp, vp, dbl, vp, vp, dbl, vp, sz, vp]
+    L.e2e_ctc_scale_rows_device.argtypes = [dp, vp, vp, i32, vp]
     L.e2e_ctc_loss_reduce_device.argtypes = [vp, i32, i32, dbl, vp, vp, vp]
     L.e2e_ctc_loss_check_device.argtypes = [vp, ctypes.POINTER(i32), vp]
     L.e2e_ctc_greedy_workspace_bytes.argtypes = [dp]
@@ -89,7 +91,7 @@ def load():
     L.e2e_ctc_profile_enable.argtypes = [i32]
     L.e2e_ctc_profile_read.argtypes = [ctypes.POINTER(dbl), ctypes.POINTER(ctypes.c_uint64), i32]
     for name in ("e2e_ctc_get_limits", "e2e_ctc_loss_forward_device", "e2e_ctc_loss_backward_device",
-                 "e2e_ctc_loss_fwd_bwd_device", "e2e_ctc_loss_reduce_device", "e2e_ctc_loss_check_device",
+                 "e2e_ctc_loss_fwd_bwd_device", "e2e_ctc_loss_step_device", "e2e_ctc_scale_rows_device", "e2e_ctc_loss_reduce_device", "e2e_ctc_loss_check_device",
                  "e2e_ctc_greedy_decode_device", "e2e_ctc_engine_create", "e2e_ctc_engine_loss_host",
                  "e2e_ctc_engine_greedy_host", "e2e_ctc_engine_last_traffic", "e2e_ctc_profile_enable",
                  "e2e_ctc_profile_read"):

@@ -65,7 +65,7 @@ static int env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
-constexpr int kMaxTargets = (kMaxLatticeWarps * 32 * 8 - 1) / 2;  // K=8: 3072 cells -> L <= 1535
+constexpr int kMaxTargets = (2 * 32 * kMaxCellsPerLane - 1) / 2;  // 2 warps x 40 cells per lane = 2560 cells -> L <= 1279
 constexpr int kMaxAlphabet = 32768;
 
 static int check_desc(const e2e_ctc_desc* d, bool need_targets) {
@@ -98,41 +98,78 @@ static int check_desc(const e2e_ctc_desc* d, bool need_targets) {
   return E2E_OK;
 }
 
-bool make_loss_plan(const e2e_ctc_desc& d, LossPlan* p) {
+static inline int align16i(size_t x) { return (int)((x + 15) & ~(size_t)15); }
+
+bool make_loss_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
+  // (cells per lane, lattice warps) variants the lattice kernel is instantiated for, by capacity.
+  // A single warp issues at most ~0.5 instructions per cycle, so when the batch is too small to fill the
+  // SMs with independent utterances (latency mode) the lattice is spread over up to 4 warps with few
+  // cells per lane; with many utterances per SM (throughput mode) one warp per sweep avoids the
+  // per-frame named barrier and leaves the issue slots to other CTAs.
+  static const int kLatency[][2] = {{2, 1}, {2, 2}, {2, 4}, {4, 4}, {8, 4}, {16, 4}, {40, 2}};
+  static const int kThroughput[][2] = {{2, 1}, {4, 1}, {8, 1}, {16, 1}, {24, 1}, {40, 1}, {40, 2}};
   const int S = 2 * d.max_targets + 1;
-  int K = env_int("E2E_CTC_CELLS_PER_LANE", 0);
-  if (K != 2 && K != 4 && K != 8) K = (S <= 128) ? 2 : (S <= 1024 ? 4 : 8);
-  while (K < 8 && ((S + K - 1) / K + 31) / 32 > kMaxLatticeWarps) K *= 2;
-  const int NW = ((S + K - 1) / K + 31) / 32;
-  if (NW > kMaxLatticeWarps) return false;
+  int mode = env_int("E2E_CTC_LATENCY_MODE", -1);
+  if (mode != 0 && mode != 1) mode = d.batch <= 148 ? 1 : 0;
+  const int (*tab)[2] = mode ? kLatency : kThroughput;
+  int K = 0, NW = 1;
+  const int fk = env_int("E2E_CTC_CELLS_PER_LANE", 0), fw = env_int("E2E_CTC_LATTICE_WARPS", 0);
+  if (fk || fw) {   // testing hook: force a variant if it exists and is large enough
+    static const int kAll[][2] = {{2, 1}, {4, 1}, {8, 1}, {16, 1}, {24, 1}, {40, 1}, {2, 2}, {40, 2}, {2, 4}, {4, 4}, {8, 4}, {16, 4}};
+    for (const auto& v : kAll)
+      if ((!fk || v[0] == fk) && (!fw || v[1] == fw) && 32 * v[0] * v[1] >= S && !K) { K = v[0]; NW = v[1]; }
+  }
+  if (!K) for (int i = 0; i < 7; i++) if (32 * tab[i][0] * tab[i][1] >= S) { K = tab[i][0]; NW = tab[i][1]; break; }
+  if (!K) return false;
   p->K = K; p->NW = NW; p->cells = 32 * K * NW; p->lanes = 32 * NW;
-  // emission staging: by symbol when the alphabet is no larger than the label row, else by label
-  p->dense = d.alphabet <= d.max_targets + 1;
+  p->words = (K + 1 + 3) & ~3;
+  // dense (fused) mode: whole rows staged by symbol; the kernel also does the log-softmax statistics and
+  // writes the gradient.  Otherwise emissions are gathered by label and K1 / K3 run around the lattice.
+  p->dense = fused && d.alphabet <= kDenseMaxAlphabet && env_int("E2E_CTC_NO_FUSED", 0) == 0;
   p->rowlen = p->dense ? d.alphabet : d.max_targets + 1;
-  p->lstride = (p->rowlen + 1 + 1) & ~1;
-  const size_t slot = d.dtype == E2E_F64 ? 32 : 16;
-  auto smem_of = [&](int cs) {
-    const size_t ring = (size_t)4 << cs;
-    return ring * p->lstride * 8 + ring * p->rowlen * slot + 64 * 32 + 33 * 8 + 16 * 8 + 36 * 4 +
-           (size_t)d.max_targets * 4 + 64;
+  p->lstride = p->dense ? ((d.alphabet + 2 + 1) & ~1) : (2 + p->cells / 2);
+  p->post_stride = p->cells / 2 + 4;
+  p->vpad = p->dense ? ((d.alphabet + 3) & ~3) : 0;
+  p->np = (p->dense && mode) ? 4 : (p->rowlen <= 32 ? 1 : (p->rowlen <= 64 ? 2 : 4));
+  p->nc = (mode && K < 24) ? 4 : 2;   // the big-K variants are compiled for at most 2 combiner warps
+  p->pfd = 8 / p->nc;
+  const size_t rawsz = d.dtype == E2E_F64 ? 8 : 4;
+  auto layout = [&](int cs, LatticeSmem* L) {
+    const size_t ring = (size_t)kNumChunks << cs;
+    size_t off = 0;
+    L->lab = (int)off; off = align16i(off + (size_t)(p->cells / 2) * 4 + 4);      // labels, padded with blank to cells/2
+    L->misc = (int)off; off += 64 + 8 * 4 * kMaxProducerWarps;   // 4 ints, then the producers' log-sum-exp partials at +64
+    L->E = (int)off; off = align16i(off + ring * p->lstride * 8);
+    L->raw = (int)off; off = align16i(off + ring * p->rowlen * rawsz);
+    L->rstat = (int)off; off += ring * 16;
+    L->val = (int)off; off += ring * p->lanes * p->words * 4;
+    L->stage = (int)off; off += (size_t)p->nc * p->pfd * p->lanes * p->words * 4;
+    L->acc = (int)off; off = align16i(off + ring * p->vpad * 4);
+    L->bnd = (int)off; off += 16 * sizeof(Boundary);
+    L->red = (int)off; off += 256;
+    L->bars = (int)off; off += 128;
+    L->total = (int)off;
+    return off;
   };
   int cs = env_int("E2E_CTC_CHUNK_LOG2", -1);
   if (cs < 0 || cs > 3) {  // aim at ~256 staged items per hand-off
     cs = 3;
     while (cs > 0 && (p->rowlen << cs) > 256) --cs;
   }
-  while (cs > 0 && smem_of(cs) > 160 * 1024) --cs;
-  if (smem_of(cs) > 220 * 1024) return false;
+  LatticeSmem L;
+  // latency mode runs one CTA per SM anyway; throughput mode wants several CTAs resident per SM
+  while (cs > 0 && layout(cs, &L) > (size_t)(mode ? 160 : 72) * 1024) --cs;
+  if (layout(cs, &L) > 220 * 1024) return false;
   p->chunk_log2 = cs;
-  p->smem = smem_of(cs);
+  p->sm = L;
+  p->smem = (size_t)L.total;
   const size_t rows = (size_t)d.batch * d.max_frames;
   size_t off = 0;
   p->off_status = off; off += 256;
   p->off_flags = off; off += align256((size_t)d.batch * 4);
-  p->off_stats = off; off += align256(rows * (d.dtype == E2E_F64 ? 16 : 8));
-  p->off_hv = off; off += align256(rows * p->cells * 4);
-  p->off_he = off; off += align256(rows * p->lanes * 4);
-  p->off_post = off; off += align256(rows * p->cells * 4);
+  p->off_stats = off; off += p->dense ? 0 : align256(rows * (d.dtype == E2E_F64 ? 16 : 8));
+  p->off_stash = off; off += align256(rows * p->lanes * p->words * 4);
+  p->off_post = off; off += p->dense ? 0 : align256(rows * p->post_stride * 4);
   p->total = off;
   return true;
 }
@@ -143,12 +180,27 @@ static int check_ws(const void* ws, size_t have, size_t need) {
   return E2E_OK;
 }
 
+// split path: K1 row statistics + lattice (gather mode; posteriors left in the workspace for K3)
 static int loss_forward(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
                         const void* in_len, const void* tgt_len, void* losses, char* ws, cudaStream_t s) {
   E2E_CUDA_TRY(cudaMemsetAsync(ws + p.off_status, 0, 256, s));
   int rc = launch_row_stats(d, logits, ws + p.off_stats, s);
   if (rc != E2E_OK) return rc;
-  return launch_lattice(d, p, logits, targets, in_len, tgt_len, losses, ws, s);
+  return launch_lattice(d, p, logits, targets, in_len, tgt_len, losses, nullptr, 1.0, ws, s);
+}
+
+// loss + gradient (scale folded in) in as few launches as the shape allows:
+// dense shapes: ONE kernel; otherwise K1 + lattice + K3
+static int loss_fwd_bwd(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
+                        const void* in_len, const void* tgt_len, void* losses, void* grads, double scale,
+                        char* ws, cudaStream_t s) {
+  if (p.dense) {
+    E2E_CUDA_TRY(cudaMemsetAsync(ws + p.off_status, 0, 256, s));
+    return launch_lattice(d, p, logits, targets, in_len, tgt_len, losses, grads, scale, ws, s);
+  }
+  int rc = loss_forward(d, p, logits, targets, in_len, tgt_len, losses, ws, s);
+  if (rc != E2E_OK) return rc;
+  return launch_grad(d, p, logits, targets, in_len, tgt_len, nullptr, 0, scale, grads, ws, s);
 }
 
 // ---- host-buffer engine -------------------------------------------------------------------------
@@ -205,6 +257,9 @@ int e2e_ctc_profile_read(double* ms, uint64_t* launches, int32_t n_kinds) {
   return E2E_OK;
 }
 
+/* debugging aid (not part of the public header): clock stamps recorded with E2E_CTC_TRACE=1 */
+int e2e_ctc_debug_trace_read(long long* host, size_t n) { return lattice_trace_read(host, n); }
+
 int e2e_ctc_get_limits(e2e_ctc_limits* out) {
   if (!out) { set_error("null limits"); return E2E_ERR_INVALID_ARGUMENT; }
   out->max_alphabet = kMaxAlphabet;
@@ -217,8 +272,9 @@ int e2e_ctc_get_limits(e2e_ctc_limits* out) {
 size_t e2e_ctc_loss_workspace_bytes(const e2e_ctc_desc* desc) {
   if (check_desc(desc, true) != E2E_OK) return 0;
   LossPlan p;
-  if (!make_loss_plan(*desc, &p)) { set_error("no lattice configuration for max_targets=%d", desc->max_targets); return 0; }
-  return p.total;
+  LossPlan q;
+  if (!make_loss_plan(*desc, false, &p) || !make_loss_plan(*desc, true, &q)) { set_error("no lattice configuration for max_targets=%d", desc->max_targets); return 0; }
+  return p.total > q.total ? p.total : q.total;
 }
 
 int e2e_ctc_loss_forward_device(const e2e_ctc_desc* desc, const void* logits, const void* targets,
@@ -231,7 +287,7 @@ int e2e_ctc_loss_forward_device(const e2e_ctc_desc* desc, const void* logits, co
     return E2E_ERR_INVALID_ARGUMENT;
   }
   LossPlan p;
-  if (!make_loss_plan(*desc, &p)) { set_error("no lattice configuration for max_targets=%d", desc->max_targets); return E2E_ERR_UNSUPPORTED; }
+  if (!make_loss_plan(*desc, false, &p)) { set_error("no lattice configuration for max_targets=%d", desc->max_targets); return E2E_ERR_UNSUPPORTED; }
   rc = check_ws(workspace, workspace_bytes, p.total);
   if (rc != E2E_OK) return rc;
   return loss_forward(*desc, p, logits, targets, logits_lengths, targets_lengths, losses,
@@ -253,7 +309,7 @@ int e2e_ctc_loss_backward_device(const e2e_ctc_desc* desc, const void* logits, c
     return E2E_ERR_INVALID_ARGUMENT;
   }
   LossPlan p;
-  if (!make_loss_plan(*desc, &p)) { set_error("no lattice configuration"); return E2E_ERR_UNSUPPORTED; }
+  if (!make_loss_plan(*desc, false, &p)) { set_error("no lattice configuration"); return E2E_ERR_UNSUPPORTED; }
   rc = check_ws(workspace, workspace_bytes, p.total);
   if (rc != E2E_OK) return rc;
   return launch_grad(*desc, p, logits, targets, logits_lengths, targets_lengths, grad_out, grad_out_count,
@@ -261,14 +317,50 @@ int e2e_ctc_loss_backward_device(const e2e_ctc_desc* desc, const void* logits, c
                      reinterpret_cast<cudaStream_t>(cuda_stream));
 }
 
+static int step_impl(const e2e_ctc_desc* desc, const void* logits, const void* targets, const void* logits_lengths,
+                     const void* targets_lengths, void* losses, void* grads, double grad_scale, void* reduced,
+                     double* reduced_f64, double reduce_scale, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+  int rc = check_desc(desc, true);
+  if (rc != E2E_OK) return rc;
+  if (!logits || !logits_lengths || !targets_lengths || !losses || !grads || (!targets && desc->max_targets > 0)) {
+    set_error("null pointer argument");
+    return E2E_ERR_INVALID_ARGUMENT;
+  }
+  LossPlan p;
+  if (!make_loss_plan(*desc, true, &p)) { set_error("no lattice configuration for max_targets=%d", desc->max_targets); return E2E_ERR_UNSUPPORTED; }
+  rc = check_ws(workspace, workspace_bytes, p.total);
+  if (rc != E2E_OK) return rc;
+  rc = loss_fwd_bwd(*desc, p, logits, targets, logits_lengths, targets_lengths, losses, grads, grad_scale,
+                    reinterpret_cast<char*>(workspace), s);
+  if (rc != E2E_OK) return rc;
+  if (reduced || reduced_f64) return launch_reduce(losses, desc->dtype, desc->batch, reduce_scale, reduced, reduced_f64, s);
+  return E2E_OK;
+}
+
 int e2e_ctc_loss_fwd_bwd_device(const e2e_ctc_desc* desc, const void* logits, const void* targets,
                                 const void* logits_lengths, const void* targets_lengths, void* losses,
                                 void* grads, void* workspace, size_t workspace_bytes, void* cuda_stream) {
-  int rc = e2e_ctc_loss_forward_device(desc, logits, targets, logits_lengths, targets_lengths, losses,
-                                       workspace, workspace_bytes, cuda_stream);
+  return step_impl(desc, logits, targets, logits_lengths, targets_lengths, losses, grads, 1.0, nullptr, nullptr, 1.0,
+                   workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+int e2e_ctc_loss_step_device(const e2e_ctc_desc* desc, const void* logits, const void* targets,
+                             const void* logits_lengths, const void* targets_lengths, void* losses,
+                             void* grads, double grad_scale, void* reduced, double* reduced_f64,
+                             double reduce_scale, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  return step_impl(desc, logits, targets, logits_lengths, targets_lengths, losses, grads, grad_scale, reduced,
+                   reduced_f64, reduce_scale, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+int e2e_ctc_scale_rows_device(const e2e_ctc_desc* desc, void* grads, const void* grad_out, int32_t grad_out_count,
+                              void* cuda_stream) {
+  int rc = check_desc(desc, false);
   if (rc != E2E_OK) return rc;
-  return e2e_ctc_loss_backward_device(desc, logits, targets, logits_lengths, targets_lengths, nullptr, 0,
-                                      1.0, grads, workspace, workspace_bytes, cuda_stream);
+  if (!grads || !grad_out || (grad_out_count != 1 && grad_out_count != desc->batch)) {
+    set_error("scale_rows: grads / grad_out required, grad_out_count must be 1 or B");
+    return E2E_ERR_INVALID_ARGUMENT;
+  }
+  return launch_scale_rows(*desc, grads, grad_out, grad_out_count, reinterpret_cast<cudaStream_t>(cuda_stream));
 }
 
 int e2e_ctc_loss_reduce_device(const void* losses, int32_t dtype, int32_t batch, double scale, void* out,
@@ -357,7 +449,7 @@ int e2e_ctc_engine_loss_host(e2e_ctc_engine* e, const e2e_ctc_desc* desc, const 
     return E2E_ERR_INVALID_ARGUMENT;
   }
   LossPlan p;
-  if (!make_loss_plan(d, &p)) { set_error("no lattice configuration for max_targets=%d", d.max_targets); return E2E_ERR_UNSUPPORTED; }
+  if (!make_loss_plan(d, true, &p)) { set_error("no lattice configuration for max_targets=%d", d.max_targets); return E2E_ERR_UNSUPPORTED; }
   E2E_CUDA_TRY(cudaSetDevice(e->device));
   const size_t es = elem_size(d.dtype);
   const size_t n_log = (size_t)d.batch * d.max_frames * d.alphabet * es;
@@ -373,11 +465,8 @@ int e2e_ctc_engine_loss_host(e2e_ctc_engine* e, const e2e_ctc_desc* desc, const 
   if (n_tgt) E2E_CUDA_TRY(cudaMemcpyAsync(e->targets.p, targets, n_tgt, cudaMemcpyHostToDevice, s));
   E2E_CUDA_TRY(cudaMemcpyAsync(e->in_len.p, logits_lengths, n_len, cudaMemcpyHostToDevice, s));
   E2E_CUDA_TRY(cudaMemcpyAsync(e->tgt_len.p, targets_lengths, n_len, cudaMemcpyHostToDevice, s));
-  rc = loss_forward(d, p, e->logits.p, e->targets.p, e->in_len.p, e->tgt_len.p, e->losses.p,
+  rc = loss_fwd_bwd(d, p, e->logits.p, e->targets.p, e->in_len.p, e->tgt_len.p, e->losses.p, e->grads.p, 1.0,
                     reinterpret_cast<char*>(e->ws.p), s);
-  if (rc != E2E_OK) return rc;
-  rc = launch_grad(d, p, e->logits.p, e->targets.p, e->in_len.p, e->tgt_len.p, nullptr, 0, 1.0, e->grads.p,
-                   reinterpret_cast<const char*>(e->ws.p), s);
   if (rc != E2E_OK) return rc;
   E2E_CUDA_TRY(cudaMemcpyAsync(losses, e->losses.p, n_loss, cudaMemcpyDeviceToHost, s));
   E2E_CUDA_TRY(cudaMemcpyAsync(grads, e->grads.p, n_log, cudaMemcpyDeviceToHost, s));

@@ -9,27 +9,49 @@
 
 namespace e2e {
 
-// ------------------------------------------------------------------ workspace layout ----------
+// ------------------------------------------------------------------ lattice kernel plan -------
+constexpr int kNumChunks = 4;          // emission / state ring depth, in chunks of 2^chunk_log2 frames
+constexpr int kMaxCombinerWarps = 4;
+constexpr int kMaxProducerWarps = 4;
+constexpr int kMaxCellsPerLane = 40;
+constexpr int kMaxLatticeWarps = 4;    // lattice warps per sweep
+constexpr int kDenseMaxAlphabet = 128; // fused ("dense") mode stages whole rows: <= 4 symbols per producer lane
+constexpr int kNegExp = -(1 << 28);    // block exponent of an all-zero lane
+
+struct __align__(16) Boundary {        // cells a lattice warp hands to its neighbour warp (NW > 1)
+  double x0, x1;
+  int e, pad0, pad1, pad2;
+};
+
+// byte offsets of the lattice kernel's dynamic shared memory regions (computed once, on the host)
+struct LatticeSmem {
+  int lab, misc, E, raw, rstat, val, stage, acc, bnd, red, bars, total;
+};
+
 // One forward call leaves everything the backward needs in the caller's workspace.
 struct LossPlan {
   int K;            // lattice cells per lane (even: cells alternate blank,label)
-  int NW;           // lattice warps per CTA
-  int cells;        // 32*K*NW  >= 2*Lmax+1   (row stride of post / hv)
-  int lanes;        // 32*NW                  (row stride of he)
-  int dense;        // emission ring indexed by symbol (V <= Lmax+1) instead of by label position
+  int NW;           // lattice warps per sweep
+  int cells;        // 32*K*NW  >= 2*Lmax+1
+  int lanes;        // 32*NW
+  int words;        // u32 words per lane per frame in the state rows: K cells + exponent, padded to 4
+  int dense;        // fused mode: whole rows staged, log-softmax + gradient write inside the lattice kernel
+  int np;           // producer warps per CTA
+  int nc;           // combiner warps per CTA (power of two)
+  int pfd;          // stashed rows each combiner warp keeps in flight (cp.async)
   int rowlen;       // emissions staged per frame: V (dense) or Lmax+1 (gather)
-  int chunk_log2;   // frames per producer hand-off = 1 << chunk_log2; the ring holds 4 chunks
-  int lstride;      // doubles per ring frame (rowlen + zero slot, rounded up to even)
+  int chunk_log2;   // frames per hand-off = 1 << chunk_log2; the rings hold kNumChunks chunks
+  int lstride;      // doubles per emission-ring frame
+  int post_stride;  // floats per frame of the compact posterior rows (gather mode): cells/2 labels + blank
+  int vpad;         // dense mode: u32 accumulators per frame
+  LatticeSmem sm;
   size_t smem;      // dynamic shared memory of the lattice kernel
   // byte offsets into the workspace
-  size_t off_status, off_flags, off_stats, off_hv, off_he, off_post, total;
+  size_t off_status, off_flags, off_stats, off_stash, off_post, total;
 };
 
-bool make_loss_plan(const e2e_ctc_desc& d, LossPlan* p);
-
-constexpr int kProducerWarps = 4;
-constexpr int kMaxLatticeWarps = 12;  // lattice warps per CTA (keeps the kernel at <=128 registers/thread)
-constexpr int kNegExp = -(1 << 28);  // block exponent of an all-zero lane
+// fused: the caller wants loss + gradient in one pass (dense mode is used when the shape allows it)
+bool make_loss_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p);
 
 // status word bits (device-side argument check)
 constexpr int kBadFrames = 1, kBadTargetLen = 2, kBadLabel = 4;
@@ -39,7 +61,7 @@ constexpr int kFlagInfeasible = 1, kFlagInvalid = 2;
 void set_error(const char* fmt, ...);
 
 // Launch accounting + optional per-kernel device timing (CUDA events on the launching stream).
-enum { kKernelRowStats = 0, kKernelLattice, kKernelGrad, kKernelReduce, kKernelArgmax, kKernelCollapse, kNumKernels };
+enum { kKernelRowStats = 0, kKernelLattice, kKernelGrad, kKernelReduce, kKernelArgmax, kKernelCollapse, kKernelScale, kNumKernels };
 void launch_begin(int kind, cudaStream_t s);
 void launch_end(int kind, cudaStream_t s);
 struct KernelTimer {   // brackets exactly one kernel launch
@@ -69,6 +91,7 @@ template <typename T> struct Elem;
 template <> struct Elem<float> {
   using acc_t = float;
   static __device__ __forceinline__ float load(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ float get(float v) { return v; }
   static __device__ __forceinline__ void store(float* p, float v) { *p = v; }
 };
 template <> struct Elem<__nv_bfloat16> {
@@ -76,16 +99,19 @@ template <> struct Elem<__nv_bfloat16> {
   static __device__ __forceinline__ float load(const __nv_bfloat16* p) {
     return __bfloat162float(__ldg(p));
   }
+  static __device__ __forceinline__ float get(__nv_bfloat16 v) { return __bfloat162float(v); }
   static __device__ __forceinline__ void store(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 };
 template <> struct Elem<__half> {
   using acc_t = float;
   static __device__ __forceinline__ float load(const __half* p) { return __half2float(__ldg(p)); }
+  static __device__ __forceinline__ float get(__half v) { return __half2float(v); }
   static __device__ __forceinline__ void store(__half* p, float v) { *p = __float2half_rn(v); }
 };
 template <> struct Elem<double> {
   using acc_t = double;
   static __device__ __forceinline__ double load(const double* p) { return __ldg(p); }
+  static __device__ __forceinline__ double get(double v) { return v; }
   static __device__ __forceinline__ void store(double* p, double v) { *p = v; }
 };
 
@@ -149,10 +175,13 @@ __device__ __forceinline__ int warp_max_int(int v) {
 // ------------------------------------------------------------------ kernel launchers ----------
 int launch_row_stats(const e2e_ctc_desc& d, const void* logits, void* stats, cudaStream_t s);
 int launch_lattice(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
-                   const void* in_len, const void* tgt_len, void* losses, char* ws, cudaStream_t s);
+                   const void* in_len, const void* tgt_len, void* losses, void* grads, double scale, char* ws,
+                   cudaStream_t s);
 int launch_grad(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
                 const void* in_len, const void* tgt_len, const void* grad_out, int grad_out_count,
                 double host_scale, void* grads, const char* ws, cudaStream_t s);
+int lattice_trace_read(long long* host, size_t n);
+int launch_scale_rows(const e2e_ctc_desc& d, void* grads, const void* grad_out, int grad_out_count, cudaStream_t s);
 int launch_reduce(const void* losses, int dtype, int B, double scale, void* out, double* out64,
                   cudaStream_t s);
 int launch_greedy(const e2e_ctc_desc& d, const void* logits, const void* in_len, int64_t* decoded,

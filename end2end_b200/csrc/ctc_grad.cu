@@ -26,7 +26,7 @@ struct GradParams {
   const void* targets; int tgt_is64; long long ts_b;
   const void* in_len; const void* tgt_len; int len_is64;
   const void* grad_out; int grad_out_count; double host_scale;
-  int B, T, V, Lmax, blank, from_logits, cells, rows_per_block;
+  int B, T, V, Lmax, blank, from_logits, cells, post_stride, rows_per_block;
 };
 
 __device__ __forceinline__ float exp_acc(float x) { return expf(x); }
@@ -83,16 +83,10 @@ ctc_grad_kernel(const GradParams p) {
   float* acc = s_acc + (size_t)w * p.V;
   for (int v = lane; v < p.V; v += 32) acc[v] = 0.f;
   __syncwarp();
-  const int S = 2 * Li + 1;
-  const float* post = p.post + row * p.cells;
-  float blank_part = 0.f;
-  for (int s = lane; s < S; s += 32) {
-    const float pv = __ldcg(post + s);
-    if (s & 1) atomicAdd(&acc[s_lab[s >> 1]], pv);
-    else blank_part += pv;
-  }
-  blank_part = warp_sum(blank_part);
-  if (lane == 0) atomicAdd(&acc[p.blank], blank_part);
+  // compact posterior row written by the lattice kernel's combiners: [label 0 .. label L-1 | ... | blank total]
+  const float* post = p.post + row * p.post_stride;
+  for (int li = lane; li < Li; li += 32) atomicAdd(&acc[s_lab[li]], __ldcg(post + li));
+  if (lane == 0) atomicAdd(&acc[p.blank], __ldcg(post + p.cells / 2));
   __syncwarp();
 
   acc_t m = 0, ls = 0;
@@ -147,7 +141,51 @@ ctc_loss_reduce_kernel(const void* losses, int dtype, int B, double scale, void*
   }
 }
 
+// ---- in-place gradient scaling by the upstream gradient (functions/forward_backward.py:34) -------
+// The fused forward already wrote scale * d loss / d logits; autograd's grad_output is almost always
+// exactly 1, which only the device knows: every block checks its utterance's factor first and leaves
+// without touching memory when it is 1.  NaN blocks stay NaN (NaN * 0 = NaN, as in the reference).
+template <typename T>
+__global__ void __launch_bounds__(256)
+ctc_scale_rows_kernel(T* grads, long long gsb, long long gst, int T_, int V, const T* grad_out, int count) {
+  using acc_t = typename Elem<T>::acc_t;
+  const int b = blockIdx.y;
+  const acc_t g = Elem<T>::load(grad_out + (count == 1 ? 0 : b));
+  if (g == (acc_t)1) return;
+  const long long n = (long long)T_ * V;
+  for (long long k = (long long)blockIdx.x * 256 + threadIdx.x; k < n; k += (long long)gridDim.x * 256) {
+    const long long t = k / V, v = k - t * V;
+    T* q = grads + b * gsb + t * gst + v;
+    Elem<T>::store(q, Elem<T>::get(*q) * g);
+  }
+}
+
+template <typename T>
+int launch_scale_typed(const e2e_ctc_desc& d, void* grads, const void* grad_out, int count, cudaStream_t s) {
+  const long long n = (long long)d.max_frames * d.alphabet;
+  unsigned gx = (unsigned)((n + 256 * 8 - 1) / (256 * 8));
+  if (gx < 1) gx = 1;
+  if (gx > 64) gx = 64;
+  KernelTimer timer(kKernelScale, s);
+  ctc_scale_rows_kernel<T><<<dim3(gx, (unsigned)d.batch), 256, 0, s>>>(
+      reinterpret_cast<T*>(grads), d.grads_stride_b, d.grads_stride_t, d.max_frames, d.alphabet,
+      reinterpret_cast<const T*>(grad_out), count);
+  E2E_CUDA_TRY(cudaGetLastError());
+  return E2E_OK;
+}
+
 }  // namespace
+
+int launch_scale_rows(const e2e_ctc_desc& d, void* grads, const void* grad_out, int grad_out_count, cudaStream_t s) {
+  switch (d.dtype) {
+    case E2E_F32: return launch_scale_typed<float>(d, grads, grad_out, grad_out_count, s);
+    case E2E_BF16: return launch_scale_typed<__nv_bfloat16>(d, grads, grad_out, grad_out_count, s);
+    case E2E_F16: return launch_scale_typed<__half>(d, grads, grad_out, grad_out_count, s);
+    case E2E_F64: return launch_scale_typed<double>(d, grads, grad_out, grad_out_count, s);
+  }
+  set_error("scale_rows: unsupported dtype %d", d.dtype);
+  return E2E_ERR_INVALID_ARGUMENT;
+}
 
 int launch_grad(const e2e_ctc_desc& d, const LossPlan& pl, const void* logits, const void* targets,
                 const void* in_len, const void* tgt_len, const void* grad_out, int grad_out_count,
@@ -162,7 +200,7 @@ int launch_grad(const e2e_ctc_desc& d, const LossPlan& pl, const void* logits, c
   p.in_len = in_len; p.tgt_len = tgt_len; p.len_is64 = d.lengths_itype == E2E_I64;
   p.grad_out = grad_out; p.grad_out_count = grad_out_count; p.host_scale = host_scale;
   p.B = d.batch; p.T = d.max_frames; p.V = d.alphabet; p.Lmax = d.max_targets; p.blank = d.blank_idx;
-  p.from_logits = d.from_logits; p.cells = pl.cells; p.rows_per_block = 8;
+  p.from_logits = d.from_logits; p.cells = pl.cells; p.post_stride = pl.post_stride; p.rows_per_block = 8;
   switch (d.dtype) {
     case E2E_F32: return launch_typed<float>(p, s);
     case E2E_BF16: return launch_typed<__nv_bfloat16>(p, s);

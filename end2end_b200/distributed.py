@@ -64,37 +64,39 @@ class _ShardedLossFunction(Function):
         ctx.engine, ctx.mean = engine, mean
         need_grad = ctx.needs_input_grad[1]
         B = logits.size(0)
-        if logits.is_cuda:
-            losses, state = engine.forward(logits, targets, logits_lengths, targets_lengths, from_logits)
-            ctx.state, ctx.grads = (state if need_grad else None), None
+        known = float(global_batch) if global_batch is not None else None
+        ctx.folded = 1.0 / known if (mean and known) else 1.0     # constant part of grad_output baked into the kernel
+        ctx.on_device = logits.is_cuda
+        if logits.is_cuda and need_grad:
+            _, ctx.grads, _, pair = engine.step(logits, targets, logits_lengths, targets_lengths, from_logits,
+                                                grad_scale=ctx.folded, want_pair=True)
+        elif logits.is_cuda:
+            losses, _ = engine.forward(logits, targets, logits_lengths, targets_lengths, from_logits)
+            ctx.grads = None
             pair = engine.partial_sum(losses)           # fp64 {sum, B} written by the reduce kernel
         else:
             losses, grads = engine.compute(logits, targets, logits_lengths, targets_lengths, from_logits)
-            ctx.state, ctx.grads = None, (grads if need_grad else None)
+            ctx.grads = grads if need_grad else None
             pair = torch.stack([losses.double().sum(), torch.tensor(float(B), dtype=torch.float64)])
         if group is not False and dist.is_available() and dist.is_initialized():
             dist.all_reduce(pair, op=dist.ReduceOp.SUM, group=group)   # THE collective of this path
-        if global_batch is not None:
-            ctx.inv_n = 1.0 / float(global_batch)
-            total = pair[0] * ctx.inv_n if mean else pair[0]
+        ctx.inv_n = None
+        if mean:
+            ctx.inv_n = (1.0 / known) if known else (1.0 / pair[1])
+            total = pair[0] * ctx.inv_n
         else:
-            ctx.inv_n = 1.0 / pair[1]
-            total = pair[0] * ctx.inv_n if mean else pair[0]
+            total = pair[0]
         return total.to(logits.dtype)
 
     @staticmethod
     def backward(ctx, grad_output):
-        if ctx.mean:
-            if isinstance(ctx.inv_n, float):
-                g, scale = grad_output, ctx.inv_n
-            else:
-                g, scale = grad_output * ctx.inv_n.to(grad_output.dtype), 1.0
+        g = grad_output
+        if ctx.mean and not isinstance(ctx.inv_n, float):
+            g = g * ctx.inv_n.to(g.dtype)              # global count only known after the all-reduce
+        if ctx.on_device:
+            grad = ctx.engine.scale_rows_(ctx.grads, g)
         else:
-            g, scale = grad_output, 1.0
-        if ctx.state is not None:
-            grad = ctx.engine.backward(ctx.state, g, scale)
-        else:
-            grad = ctx.grads * (g.to(ctx.grads.device).reshape(1, 1, 1) * scale)
+            grad = ctx.grads * (g.to(ctx.grads.device).reshape(1, 1, 1) * ctx.folded)
         return None, grad, None, None, None, None, None, None, None
 
 

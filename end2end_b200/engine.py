@@ -33,8 +33,31 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else ctypes.c_void_p(0)
 
 
+try:
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:  # pragma: no cover - older torch
+    def _raw_stream(index):
+        return torch.cuda.current_stream(index).cuda_stream
+
+
 def _stream(device):
-    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    return ctypes.c_void_p(_raw_stream(device.index if device.index is not None else torch.cuda.current_device()))
+
+
+class _on_device:
+    """``torch.cuda.device(dev)`` without its cost when ``dev`` is already current (the usual case)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        self.ctx = None if device.index is None or device.index == torch.cuda.current_device() else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
 
 
 def _as_index(t, device, name):
@@ -45,6 +68,16 @@ def _as_index(t, device, name):
     if t.device != device:
         t = t.to(device, non_blocking=True)
     return t
+
+
+_LIMITS = None
+
+
+def _limits():
+    global _LIMITS
+    if _LIMITS is None:
+        _LIMITS = _lib.limits()
+    return _LIMITS
 
 
 def _dense3(x):
@@ -74,7 +107,7 @@ class _Problem:
                 targets_lengths.dim() != 1 or targets_lengths.numel() != B:
             raise ValueError("length tensors must have shape [batch]")
         Lmax = targets.size(1)
-        lim = _lib.limits()
+        lim = _limits()
         if Lmax > lim.max_targets or V > lim.max_alphabet:
             raise NotImplementedError("this build supports target length <= %d and alphabet <= %d"
                                       % (lim.max_targets, lim.max_alphabet))
@@ -132,6 +165,7 @@ class CTCLossEngine:
         self.blank_idx = int(blank_idx)
         self._L = _lib.load()
         self._host = {}
+        self._ws_bytes = {}
 
     # ------------------------------------------------------------------ reference contract ----
     def compute(self, logits, targets, logits_lengths, targets_lengths, from_logits=False):
@@ -142,7 +176,7 @@ class CTCLossEngine:
         logits = logits.detach()
         if not logits.is_cuda:
             return self._compute_host(logits, targets, logits_lengths, targets_lengths, from_logits)
-        with torch.cuda.device(logits.device):
+        with _on_device(logits.device):
             pb = _Problem(self.blank_idx, logits, targets, logits_lengths, targets_lengths, from_logits, logits.device)
             losses = torch.empty(pb.B, dtype=logits.dtype, device=logits.device)
             grads = pb.new_grads()
@@ -152,12 +186,54 @@ class CTCLossEngine:
                 _ptr(pb.targets_lengths), _ptr(losses), _ptr(grads), _ptr(ws), ws.numel(), _stream(logits.device)))
         return losses, grads
 
+    # ------------------------------------------------------------------ one training step -------
+    def step(self, logits, targets, logits_lengths, targets_lengths, from_logits=False, grad_scale=1.0,
+             reduce_scale=None, want_pair=False):
+        """Loss and gradient of one batch in ONE library call (device tensors).
+
+        Returns ``(losses[B], grads, reduced, pair)``: ``grads = grad_scale * d loss_b / d logits``;
+        ``reduced`` is the 0-dim ``reduce_scale * sum(losses)`` (``None`` if ``reduce_scale`` is None);
+        ``pair`` the fp64 ``[sum(losses), B]`` a data-parallel caller all-reduces (``want_pair``).
+        Alphabets <= 128 run as a single fused kernel (+ the reduction)."""
+        _require_cuda()
+        logits = logits.detach()
+        dev = logits.device
+        with _on_device(dev):
+            pb = _Problem(self.blank_idx, logits, targets, logits_lengths, targets_lengths, from_logits, dev)
+            losses = torch.empty(pb.B, dtype=logits.dtype, device=dev)
+            grads = pb.new_grads()
+            reduced = torch.empty((), dtype=logits.dtype, device=dev) if reduce_scale is not None else None
+            pair = torch.empty(2, dtype=torch.float64, device=dev) if want_pair else None
+            ws = self._workspace(pb)
+            _lib.check(self._L.e2e_ctc_loss_step_device(
+                ctypes.byref(pb.desc), _ptr(pb.logits), _ptr(pb.targets), _ptr(pb.logits_lengths),
+                _ptr(pb.targets_lengths), _ptr(losses), _ptr(grads), float(grad_scale), _ptr(reduced), _ptr(pair),
+                float(reduce_scale if reduce_scale is not None else 1.0), _ptr(ws), ws.numel(), _stream(dev)))
+        return losses, grads, reduced, pair
+
+    def scale_rows_(self, grads, grad_output):
+        """``grads[b] *= grad_output[b or 0]`` in place (functions/forward_backward.py:34); utterances whose
+        factor is exactly 1 are skipped on the device."""
+        dev = grads.device
+        g = grad_output.detach().to(device=dev, dtype=grads.dtype).contiguous()
+        if g.numel() not in (1, grads.size(0)):
+            raise ValueError("grad_output must have 1 or batch elements")
+        d = _lib.Desc()
+        d.batch, d.max_frames, d.alphabet, d.max_targets = grads.size(0), grads.size(1), grads.size(2), 0
+        d.blank_idx, d.dtype = 0, _DTYPES[grads.dtype]
+        d.targets_itype = d.lengths_itype = _lib.E2E_I64
+        d.grads_stride_b, d.grads_stride_t = grads.stride(0), grads.stride(1)
+        d.logits_stride_b, d.logits_stride_t = grads.stride(0), grads.stride(1)
+        with _on_device(dev):
+            _lib.check(self._L.e2e_ctc_scale_rows_device(ctypes.byref(d), _ptr(grads), _ptr(g), g.numel(), _stream(dev)))
+        return grads
+
     # ------------------------------------------------------------------ split halves (device) --
     def forward(self, logits, targets, logits_lengths, targets_lengths, from_logits=False):
         """Per-utterance losses [B] and an opaque state for :meth:`backward` (device tensors only)."""
         _require_cuda()
         logits = logits.detach()
-        with torch.cuda.device(logits.device):
+        with _on_device(logits.device):
             pb = _Problem(self.blank_idx, logits, targets, logits_lengths, targets_lengths, from_logits, logits.device)
             losses = torch.empty(pb.B, dtype=logits.dtype, device=logits.device)
             pb.workspace = self._workspace(pb)
@@ -171,7 +247,7 @@ class CTCLossEngine:
         """grads[b] = scale * grad_output[b or 0] * d loss_b / d logits, written in one pass."""
         pb = state
         dev = pb.logits.device
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             grads = pb.new_grads()
             count = 0
             if grad_output is not None:
@@ -188,7 +264,7 @@ class CTCLossEngine:
     def reduce(self, losses, scale=1.0):
         """0-dim ``scale * sum(losses)`` (modules/ctc_loss.py:52-56), fp64 accumulation on the device."""
         out = torch.empty((), dtype=losses.dtype, device=losses.device)
-        with torch.cuda.device(losses.device):
+        with _on_device(losses.device):
             _lib.check(self._L.e2e_ctc_loss_reduce_device(
                 _ptr(losses), _DTYPES[losses.dtype], losses.numel(), float(scale), _ptr(out),
                 ctypes.c_void_p(0), _stream(losses.device)))
@@ -198,7 +274,7 @@ class CTCLossEngine:
         """fp64 device tensor ``[sum(losses), len(losses)]`` -- the pair a data-parallel caller
         all-reduces (one 16-byte collective)."""
         pair = torch.empty(2, dtype=torch.float64, device=losses.device)
-        with torch.cuda.device(losses.device):
+        with _on_device(losses.device):
             _lib.check(self._L.e2e_ctc_loss_reduce_device(
                 _ptr(losses), _DTYPES[losses.dtype], losses.numel(), 1.0, ctypes.c_void_p(0),
                 _ptr(pair), _stream(losses.device)))
@@ -207,16 +283,20 @@ class CTCLossEngine:
     def check(self, state):
         """Device-side argument check of the forward that produced ``state`` (synchronises)."""
         st = ctypes.c_int32(0)
-        with torch.cuda.device(state.logits.device):
+        with _on_device(state.logits.device):
             _lib.check(self._L.e2e_ctc_loss_check_device(_ptr(state.workspace), ctypes.byref(st),
                                                          _stream(state.logits.device)))
         return st.value
 
     # ------------------------------------------------------------------ internals --------------
     def _workspace(self, pb):
-        n = self._L.e2e_ctc_loss_workspace_bytes(ctypes.byref(pb.desc))
-        if n == 0:
-            raise _lib.E2EError(2, self._L.e2e_last_error_string().decode("utf-8", "replace"))
+        key = (pb.B, pb.T, pb.V, pb.Lmax, pb.desc.dtype)
+        n = self._ws_bytes.get(key)
+        if n is None:
+            n = self._L.e2e_ctc_loss_workspace_bytes(ctypes.byref(pb.desc))
+            if n == 0:
+                raise _lib.E2EError(2, self._L.e2e_last_error_string().decode("utf-8", "replace"))
+            self._ws_bytes[key] = n
         return torch.empty(n, dtype=torch.uint8, device=pb.logits.device)
 
     def _host_engine(self, device):
@@ -311,7 +391,7 @@ class CTCGreedyEngine:
             logits_lengths = _as_index(logits_lengths, dev, "logits_lengths").contiguous()
         d = self._desc(logits, logits_lengths)
         B, T = logits.size(0), logits.size(1)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             decoded = torch.empty(B, T, dtype=torch.int64, device=dev)
             lengths = torch.empty(B, dtype=torch.int64, device=dev)
             ws = torch.empty(self._L.e2e_ctc_greedy_workspace_bytes(ctypes.byref(d)), dtype=torch.uint8, device=dev)

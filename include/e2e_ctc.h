@@ -118,11 +118,29 @@ int e2e_ctc_loss_backward_device(const e2e_ctc_desc* desc, const void* logits, c
                                  void* grads, void* workspace, size_t workspace_bytes,
                                  void* cuda_stream);
 
-/* Forward + backward with scale 1: exactly CTCLossEngine.compute() (ctc_loss_py.cpp:10-16). */
+/* Forward + backward with scale 1: exactly CTCLossEngine.compute() (ctc_loss_py.cpp:10-16).
+ * Shapes with alphabet <= 128 run as ONE fused kernel (row log-softmax statistics, lattice and
+ * gradient write); larger alphabets run row statistics + lattice + gradient kernels. */
 int e2e_ctc_loss_fwd_bwd_device(const e2e_ctc_desc* desc, const void* logits, const void* targets,
                                 const void* logits_lengths, const void* targets_lengths,
                                 void* losses, void* grads, void* workspace, size_t workspace_bytes,
                                 void* cuda_stream);
+
+/* One training step in one call: e2e_ctc_loss_fwd_bwd_device with the gradient scaled by
+ * `grad_scale` (1/B for a mean-reduced loss: functions/forward_backward.py:34 with the constant
+ * part of grad_output folded in), followed -- when `reduced` or `reduced_f64` is non-NULL -- by
+ * e2e_ctc_loss_reduce_device(losses, ..., reduce_scale, reduced, reduced_f64). */
+int e2e_ctc_loss_step_device(const e2e_ctc_desc* desc, const void* logits, const void* targets,
+                             const void* logits_lengths, const void* targets_lengths, void* losses,
+                             void* grads, double grad_scale, void* reduced, double* reduced_f64,
+                             double reduce_scale, void* workspace, size_t workspace_bytes,
+                             void* cuda_stream);
+
+/* grads[b,:,:] *= grad_out[b] (grad_out_count == B) or grad_out[0] (grad_out_count == 1), in
+ * place; grad_out is a device pointer of desc->dtype.  Blocks whose factor is exactly 1 return
+ * without touching memory, so autograd's usual all-ones grad_output costs one empty launch. */
+int e2e_ctc_scale_rows_device(const e2e_ctc_desc* desc, void* grads, const void* grad_out,
+                              int32_t grad_out_count, void* cuda_stream);
 
 /* out[0] = scale * sum_b losses[b]  (modules/ctc_loss.py:52-56: sum, or mean with scale = 1/B;
  * multi-GPU callers all-reduce this scalar).  losses/out are of `dtype`; summation is fp64 in a
@@ -181,7 +199,8 @@ uint64_t e2e_ctc_launch_count(void);
 /* Optional per-kernel device timing for benchmarks.  While enabled, every kernel launch is
  * bracketed by CUDA events on its launching stream.  e2e_ctc_profile_read() waits for the pending
  * events, then fills ms[k] (summed device milliseconds) and launches[k] per kernel kind
- * k = 0 row_stats, 1 lattice, 2 gradient, 3 loss_reduce, 4 argmax, 5 collapse (n_kinds >= 6),
+ * k = 0 row_stats, 1 lattice, 2 gradient, 3 loss_reduce, 4 argmax, 5 collapse, 6 scale_rows
+ * (n_kinds >= 7),
  * and clears the record.  All launches since the previous read must have been made on ONE device. */
 int e2e_ctc_profile_enable(int32_t on);
 int e2e_ctc_profile_read(double* ms, uint64_t* launches, int32_t n_kinds);

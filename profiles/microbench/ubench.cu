@@ -106,6 +106,54 @@ __global__ void lat_chain(double* out, long long* cyc, int n) {
   long long t1 = clock64();
   out[64 + threadIdx.x] = a; if (threadIdx.x == 0) cyc[0] = t1 - t0;
 }
+
+__device__ __forceinline__ void sts_v4(volatile void* p, int a, int b, int c, int d) {
+  asm volatile("st.volatile.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"((unsigned)__cvta_generic_to_shared((const void*)p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ int4 lds_v4(volatile void* p) {
+  int4 r;
+  asm volatile("ld.volatile.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"((unsigned)__cvta_generic_to_shared((const void*)p)) : "memory");
+  return r;
+}
+// two warps ping-pong through a tagged 16-byte shared-memory slot (volatile polling): one-way hop latency
+__global__ void lat_pingpong(double* out, long long* cyc, int n) {
+  __shared__ __align__(16) volatile int slot[2][4];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 8) ((volatile int*)slot)[threadIdx.x] = -1;
+  __syncthreads();
+  long long t0 = clock64();
+  double acc = out[0];
+  for (int i = 0; i < n; i++) {
+    if (w == 0) {
+      if (lane == 0) sts_v4(&slot[0][0], __double2loint(acc), __double2hiint(acc), 0, i);
+      int tag; int4 r;
+      do { r = lds_v4(&slot[1][0]); tag = r.w; } while (tag != i);
+      acc = __hiloint2double(r.y, r.x) + 1.0;
+    } else {
+      int tag; int4 r;
+      do { r = lds_v4(&slot[0][0]); tag = r.w; } while (tag != i);
+      acc = __hiloint2double(r.y, r.x) + 1.0;
+      if (lane == 0) sts_v4(&slot[1][0], __double2loint(acc), __double2hiint(acc), 0, i);
+    }
+  }
+  long long t1 = clock64();
+  out[64 + threadIdx.x] = acc; if (threadIdx.x == 0) cyc[0] = t1 - t0;
+}
+__global__ void lat_f2f(double* out, long long* cyc, int n) {
+  double a = out[threadIdx.x & 31];
+  long long t0 = clock64();
+  #pragma unroll 8
+  for (int i = 0; i < n; i++) { float f = (float)a; a = (double)f; }
+  long long t1 = clock64();
+  out[64 + threadIdx.x] = a; if (threadIdx.x == 0) cyc[0] = t1 - t0;
+}
+// named barrier between 2 / 4 warps
+__global__ void lat_namedbar(long long* cyc, int n, int nthr) {
+  long long t0 = clock64();
+  if (threadIdx.x < nthr) for (int i = 0; i < n; i++) asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+  long long t1 = clock64();
+  if (threadIdx.x == 0) cyc[0] = t1 - t0;
+}
 int main() {
   double* d; long long* c; CK(cudaMalloc(&d, 1 << 16)); CK(cudaMalloc(&c, 1 << 16)); CK(cudaMemset(d, 0, 1 << 16));
   float* f = (float*)d; int* ii = (int*)d;
@@ -125,6 +173,9 @@ int main() {
     lat_shfl32<<<1,32>>>(ii, c, n); CK(cudaMemcpy(h, c, 8, cudaMemcpyDeviceToHost)); printf("SHFL32+IADD lat    %.2f cyc\n", (double)h[0]/n);
     for (int nt = 32; nt <= 1024; nt *= 2) { lat_bar<<<1,nt>>>(c, n); CK(cudaMemcpy(h, c, 8, cudaMemcpyDeviceToHost)); printf("BAR.SYNC %4d thr   %.2f cyc\n", nt, (double)h[0]/n); }
     lat_lds<<<1,32>>>(ii, c, n); CK(cudaMemcpy(h, c, 8, cudaMemcpyDeviceToHost)); printf("LDS latency        %.2f cyc\n", (double)h[0]/n);
+    lat_pingpong<<<1,64>>>(d, c, n); CK(cudaMemcpy(h, c, 8, cudaMemcpyDeviceToHost)); printf("smem flag ping-pong round trip %.2f cyc (one-way hop = half)\n", (double)h[0]/n);
+    lat_f2f<<<1,32>>>(d, c, n); CK(cudaMemcpy(h, c, 8, cudaMemcpyDeviceToHost)); printf("F2F d->f->d pair latency %.2f cyc\n", (double)h[0]/n);
+    for (int nt = 64; nt <= 256; nt *= 2) { lat_namedbar<<<1,256>>>(c, n, nt); CK(cudaMemcpy(h, c, 8, cudaMemcpyDeviceToHost)); printf("named bar.sync %3d thr %.2f cyc\n", nt, (double)h[0]/n); }
     lat_chain<<<1,32>>>(d, c, n); CK(cudaMemcpy(h, c, 8, cudaMemcpyDeviceToHost)); printf("chain shfl64+dmul+dfma+dmul %.2f cyc\n", (double)h[0]/n);
   }
   CK(cudaDeviceSynchronize());

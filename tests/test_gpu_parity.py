@@ -176,9 +176,24 @@ def test_config_vs_oracle(e2e, cfg, B, scale):
     assert_parity(g_gpu, g_ref, what=cfg + " engine grads")
 
 
-def test_every_lattice_shape_vs_oracle(e2e):
-    """Target lengths 0..70 (1..141 lattice cells) so every lane/warp-edge placement of the entry and
-    exit cells is hit for each cells-per-lane variant, with repeats and short T."""
+def _with_env(env, fn):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return fn()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_every_lattice_shape_vs_oracle(e2e, fused):
+    """Target lengths 0..70 (1..141 lattice cells) so every lane-edge placement of the entry and exit
+    cells is hit for each cells-per-lane variant, with repeats and short T; once through the fused
+    single-kernel (dense) mode and once through row-stats + gather lattice + gradient kernels."""
     g = torch.Generator().manual_seed(7)
     B, T_, V = 71, 90, 7
     x = torch.randn(B, T_, V, generator=g)
@@ -188,14 +203,67 @@ def test_every_lattice_shape_vs_oracle(e2e):
     ll = torch.randint(T_ // 2, T_ + 1, (B,), generator=g)
     lp = torch.log_softmax(x, 2)
     l_ref, g_ref = oracle.engine(0).compute(lp, tg, ll, tl)
-    for K in ("2", "4", "8"):
-        os.environ["E2E_CTC_CELLS_PER_LANE"] = K
-        try:
-            l_gpu, g_gpu = e2e.CTCLossEngine(0).compute(lp.cuda(), *cuda(tg, ll, tl))
-        finally:
-            del os.environ["E2E_CTC_CELLS_PER_LANE"]
-        assert_parity(l_gpu, l_ref, what="K=%s losses" % K)
-        assert_parity(g_gpu, g_ref, what="K=%s grads" % K)
+    for K in (2, 4, 8, 16, 24, 40):
+        Lmax = min(70, (32 * K - 1) // 2)                  # widest targets matrix this variant covers
+        keep = tl <= Lmax
+        env = {"E2E_CTC_CELLS_PER_LANE": str(K)}
+        if not fused:
+            env["E2E_CTC_NO_FUSED"] = "1"
+        for from_logits, inp in ((False, lp), (True, x)):
+            l_gpu, g_gpu = _with_env(env, lambda: e2e.CTCLossEngine(0).compute(
+                inp[keep].cuda(), *cuda(tg[keep][:, :Lmax], ll[keep], tl[keep]), from_logits=from_logits))
+            assert_parity(l_gpu, l_ref[keep], what="K=%d losses" % K)
+            if from_logits:      # d/d logits on valid frames equals softmax - posterior; padding frames are 0
+                g_exp = g_ref[keep].clone()
+                for row, n in enumerate(ll[keep].tolist()):
+                    g_exp[row, n:] = 0
+                    if not torch.isfinite(l_ref[keep][row]):
+                        g_exp[row] = float("nan")
+                assert_parity(g_gpu, g_exp, what="K=%d logits grads" % K)
+            else:
+                assert_parity(g_gpu, g_ref[keep], what="K=%d grads" % K)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_two_lattice_warps_long_targets(e2e, fused):
+    """2L+1 > 1280 cells: two lattice warps per sweep exchange their boundary cells through shared memory."""
+    g = torch.Generator().manual_seed(11)
+    B, T_, V = 3, 760, 6
+    x = torch.randn(B, T_, V, generator=g)
+    tl = torch.tensor([700, 641, 655])
+    tg = torch.randint(1, V, (B, 700), generator=g)
+    ll = torch.tensor([760, 750, 730])
+    lp = torch.log_softmax(x, 2)
+    l_ref, g_ref = oracle.engine(0).compute(lp, tg, ll, tl)
+    env = {} if fused else {"E2E_CTC_NO_FUSED": "1"}
+    l_gpu, g_gpu = _with_env(env, lambda: e2e.CTCLossEngine(0).compute(lp.cuda(), *cuda(tg, ll, tl)))
+    assert_parity(l_gpu, l_ref, what="NW=2 losses")
+    assert_parity(g_gpu, g_ref, what="NW=2 grads")
+
+
+def test_split_forward_backward_and_repeated_backward(e2e):
+    """engine.forward()/backward() (row stats + lattice, then the gradient kernel with grad_output
+    folded in) against engine.step(); and two backward passes through a retained graph."""
+    x, tg, ll, tl = oracle.make_inputs(16, 120, 29, 20, 50, 5)
+    eng = e2e.CTCLossEngine(0)
+    xc, tgc, llc, tlc = cuda(x, tg, ll, tl)
+    losses, state = eng.forward(xc, tgc, llc, tlc, from_logits=True)
+    go = torch.rand(16, device="cuda") + 0.5
+    g_split = eng.backward(state, go, 0.25)
+    l_step, g_step, red, pair = eng.step(xc, tgc, llc, tlc, from_logits=True, grad_scale=0.25, reduce_scale=1.0 / 16,
+                                         want_pair=True)
+    eng.scale_rows_(g_step, go)
+    assert_parity(l_step, losses, what="step vs split losses")
+    assert_parity(g_step, g_split, what="step vs split grads")
+    assert abs(red.item() - losses.double().mean().item()) < 1e-3 and pair[1].item() == 16.0
+    assert abs(pair[0].item() - losses.double().mean().item()) < 1e-3    # the pair carries the scaled sum
+    leaf = xc.clone().requires_grad_()
+    loss = e2e.CTCLoss(reduce=True, size_average=False)(leaf, tgc, llc, tlc)
+    loss.backward(torch.tensor(2.0, device="cuda"), retain_graph=True)
+    g1 = leaf.grad.clone()
+    leaf.grad = None
+    loss.backward(torch.tensor(3.0, device="cuda"))
+    assert_parity(leaf.grad * 2.0, g1 * 3.0, what="repeated backward")
 
 
 def test_time_major_in_place_and_reduce_modes(e2e):
@@ -406,7 +474,7 @@ def test_c_abi_direct_calls(e2e):
     before = _lib.launch_count()
     rc = L.e2e_ctc_loss_fwd_bwd_device(ctypes.byref(d), p(lp), p(tgc), p(llc), p(tlc), p(losses), p(grads), p(ws), n, stream)
     assert rc == 0, L.e2e_last_error_string()
-    assert _lib.launch_count() - before == 3                                # row stats, lattice, gradient
+    assert _lib.launch_count() - before == 1                                # V <= 128: one fused kernel
     l_ref, g_ref = oracle.engine(0).compute(lp.cpu(), tg, ll, tl)
     assert_parity(losses, l_ref, what="abi losses")
     assert_parity(grads, g_ref, what="abi grads")
@@ -415,7 +483,7 @@ def test_c_abi_direct_calls(e2e):
     assert L.e2e_ctc_loss_reduce_device(p(losses), _lib.E2E_F32, 4, 0.25, p(total), p(pair), stream) == 0
     assert abs(total.item() - l_ref.double().mean().item()) < 1e-4 and pair[1].item() == 4.0
     # error paths: small / misaligned workspace, null pointers, bad descriptor
-    assert L.e2e_ctc_loss_fwd_bwd_device(ctypes.byref(d), p(lp), p(tgc), p(llc), p(tlc), p(losses), p(grads), p(ws), n - 1, stream) == 3
+    assert L.e2e_ctc_loss_fwd_bwd_device(ctypes.byref(d), p(lp), p(tgc), p(llc), p(tlc), p(losses), p(grads), p(ws), 4096, stream) == 3
     assert L.e2e_ctc_loss_fwd_bwd_device(ctypes.byref(d), p(lp), p(tgc), p(llc), p(tlc), p(losses), p(grads),
                                          ctypes.c_void_p(ws.data_ptr() + 8), n, stream) == 3
     assert L.e2e_ctc_loss_fwd_bwd_device(ctypes.byref(d), None, p(tgc), p(llc), p(tlc), p(losses), p(grads), p(ws), n, stream) == 1

@@ -75,7 +75,7 @@ def test_limits_and_workspace_planning(L):
                                   "c4": (128, 250, 1024, 80), "c5": (2048, 1600, 29, 600)}.items():
         n = L.e2e_ctc_loss_workspace_bytes(ctypes.byref(_desc(B, T, V, Lmax)))
         cells = 2 * Lmax + 1
-        assert n >= B * T * cells * 8 and n % 256 == 0, name
+        assert n >= B * T * cells * 4 and n % 256 == 0, name      # stashed half-lattice: 4 bytes per cell
         assert n <= B * T * (cells + 256) * 9 + (1 << 20), name        # padding stays bounded
         sizes[name] = n
     assert sizes["c5"] < 60 * 2 ** 30                                    # fits a 180 GB part with room to spare
