@@ -60,6 +60,7 @@ static inline size_t elem_size(int dtype) {
   }
   return 0;
 }
+static inline int align16i(size_t x) { return (int)((x + 15) & ~(size_t)15); }
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
@@ -98,9 +99,73 @@ static int check_desc(const e2e_ctc_desc* d, bool need_targets) {
   return E2E_OK;
 }
 
-static inline int align16i(size_t x) { return (int)((x + 15) & ~(size_t)15); }
+// One-warp-per-sweep kernel: variants by cells per lane; f64 inputs use a subset (compile time).
+static const int kSweepK[] = {2, 4, 6, 8, 10, 12, 14, 16, 20, 24, 28, 32, 36, 40};
+static const int kSweepK64[] = {2, 4, 8, 16, 24, 40};
+
+static bool make_sweep_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
+  const int S = 2 * d.max_targets + 1;
+  const bool f64 = d.dtype == E2E_F64;
+  int K = 0;
+  if (f64) { for (int k : kSweepK64) if (32 * k >= S) { K = k; break; } }
+  else { for (int k : kSweepK) if (32 * k >= S) { K = k; break; } }
+  if (!K) return false;
+  p->sweep = 1;
+  p->K = K; p->NW = 1; p->cells = 32 * K; p->lanes = 32;
+  p->words = (K + 1 + 3) & ~3;
+  p->dense = fused && d.alphabet <= kDenseMaxAlphabet && env_int("E2E_CTC_NO_FUSED", 0) == 0;
+  p->rowlen = p->dense ? d.alphabet : d.max_targets + 1;
+  p->lstride = 0; p->np = 0; p->nc = 0; p->pfd = 0; p->chunk_log2 = 0;
+  p->post_stride = p->cells / 2 + 4;
+  p->vpad = p->dense ? ((d.alphabet + 1 + 3) & ~3) : 0;
+  const int H = K / 2, PF = K >= 24 ? 2 : 8;
+  const int et = f64 ? 8 : 4;
+  const int esz = f64 ? 8 : (d.dtype == E2E_F32 ? 4 : 2);
+  SweepLayout L;
+  L.vpad = p->vpad;
+  L.es = p->dense ? ((d.alphabet + 1) | 1) : (1 + 32 * H);
+  if (f64) L.rawrow = p->rowlen * 8;
+  else if (p->dense) L.rawrow = ((((d.alphabet * esz + 2 + 3) >> 2)) | 1) * 4;
+  else L.rawrow = ((d.max_targets + 1) | 1) * 4;
+  auto layout = [&](int cf) {
+    L.cf = cf;
+    size_t off = 0;
+    L.off_lab = 0; off = (size_t)align16i((size_t)(32 * H + 1) * 4);
+    L.off_warp = (int)off;
+    size_t w = 0;
+    L.w_E = (int)w; w = (size_t)align16i(w + (size_t)cf * L.es * et);
+    L.w_raw = (int)w; w = (size_t)align16i(w + (size_t)cf * L.rawrow);
+    L.w_stat = (int)w; w += (size_t)cf * 16;
+    L.w_rs = (int)w; w = (size_t)align16i(w + (size_t)cf * 4);
+    L.w_acc = (int)w; w += (size_t)2 * L.vpad * 4;
+    L.w_stage = (int)w; w += (size_t)PF * 32 * p->words * 4;
+    L.warp_bytes = (int)w;
+    return off + 2 * w;
+  };
+  int cf = env_int("E2E_CTC_CHUNK_FRAMES", 32);
+  if (cf != 8 && cf != 16 && cf != 32) cf = 32;
+  // several CTAs per SM when the batch is large; otherwise whatever fits
+  const size_t want = d.batch > 148 ? 56 * 1024 : 200 * 1024;
+  while (cf > 8 && layout(cf) > want) cf >>= 1;
+  const size_t smem = layout(cf);
+  if (smem > 220 * 1024) return false;
+  p->sw = L;
+  p->smem = smem;
+  const size_t rows = (size_t)d.batch * d.max_frames;
+  size_t off = 0;
+  p->off_status = off; off += 256;
+  p->off_flags = off; off += align256((size_t)d.batch * 4);
+  p->off_stats = off; off += p->dense ? 0 : align256(rows * (f64 ? 16 : 8));
+  p->off_stash = off; off += align256(rows * 32 * p->words * 4);
+  p->off_post = off; off += p->dense ? 0 : align256(rows * p->post_stride * 4);
+  p->total = off;
+  return true;
+}
 
 bool make_loss_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
+  p->sweep = 0;
+  if (env_int("E2E_CTC_LEGACY", 0) == 0 && make_sweep_plan(d, fused, p)) return true;
+  p->sweep = 0;
   // (cells per lane, lattice warps) variants the lattice kernel is instantiated for, by capacity.
   // A single warp issues at most ~0.5 instructions per cycle, so when the batch is too small to fill the
   // SMs with independent utterances (latency mode) the lattice is spread over up to 4 warps with few
@@ -186,6 +251,7 @@ static int loss_forward(const e2e_ctc_desc& d, const LossPlan& p, const void* lo
   E2E_CUDA_TRY(cudaMemsetAsync(ws + p.off_status, 0, 256, s));
   int rc = launch_row_stats(d, logits, ws + p.off_stats, s);
   if (rc != E2E_OK) return rc;
+  if (p.sweep) return launch_sweep(d, p, logits, targets, in_len, tgt_len, losses, nullptr, 1.0, ws, s);
   return launch_lattice(d, p, logits, targets, in_len, tgt_len, losses, nullptr, 1.0, ws, s);
 }
 
@@ -196,6 +262,7 @@ static int loss_fwd_bwd(const e2e_ctc_desc& d, const LossPlan& p, const void* lo
                         char* ws, cudaStream_t s) {
   if (p.dense) {
     E2E_CUDA_TRY(cudaMemsetAsync(ws + p.off_status, 0, 256, s));
+    if (p.sweep) return launch_sweep(d, p, logits, targets, in_len, tgt_len, losses, grads, scale, ws, s);
     return launch_lattice(d, p, logits, targets, in_len, tgt_len, losses, grads, scale, ws, s);
   }
   int rc = loss_forward(d, p, logits, targets, in_len, tgt_len, losses, ws, s);

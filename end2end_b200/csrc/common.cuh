@@ -28,8 +28,16 @@ struct LatticeSmem {
   int lab, misc, E, raw, rstat, val, stage, acc, bnd, red, bars, total;
 };
 
+// shared-memory layout of the one-warp-per-sweep lattice kernel (ctc_sweep_impl.cuh), bytes
+struct SweepLayout {
+  int cf, es, rawrow, vpad;
+  int off_lab, off_warp, warp_bytes, w_E, w_raw, w_stat, w_rs, w_acc, w_stage;
+};
+
 // One forward call leaves everything the backward needs in the caller's workspace.
 struct LossPlan {
+  int sweep;        // 1: one-warp-per-sweep kernel (ctc_sweep_*.cu); 0: the warp-specialised cluster kernel
+  SweepLayout sw;
   int K;            // lattice cells per lane (even: cells alternate blank,label)
   int NW;           // lattice warps per sweep
   int cells;        // 32*K*NW  >= 2*Lmax+1
@@ -181,6 +189,10 @@ int launch_grad(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, co
                 const void* in_len, const void* tgt_len, const void* grad_out, int grad_out_count,
                 double host_scale, void* grads, const char* ws, cudaStream_t s);
 int lattice_trace_read(long long* host, size_t n);
+int launch_sweep(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
+                 const void* in_len, const void* tgt_len, void* losses, void* grads, double scale, char* ws,
+                 cudaStream_t s);
+constexpr int kSweepMaxCellsPerLane = 40;   // one warp covers 32 * 40 = 1280 cells: L <= 639
 int launch_scale_rows(const e2e_ctc_desc& d, void* grads, const void* grad_out, int grad_out_count, cudaStream_t s);
 int launch_reduce(const void* losses, int dtype, int B, double scale, void* out, double* out64,
                   cudaStream_t s);
