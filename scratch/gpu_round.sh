@@ -14,10 +14,10 @@ echo "== ncu launches"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 80 --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_${TAG}.log 2>&1
 tail -2 gpurun_out/ncu_launch_${TAG}.log
 echo "== ncu full (lattice c2)"
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:ctc_lattice -s 5 -c 2 -o gpurun_out/prof_lattice_c2_${TAG} -f python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_${TAG}.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"ctc_lattice|ctc_sweep" -s 5 -c 2 -o gpurun_out/prof_lattice_c2_${TAG} -f python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_${TAG}.log 2>&1
 tail -2 gpurun_out/ncu_full_${TAG}.log
 echo "== ncu full (lattice c4)"
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:ctc_lattice -s 5 -c 1 -o gpurun_out/prof_lattice_c4_${TAG} -f python bench.py --workload c4 --steps 5 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"ctc_lattice|ctc_sweep" -s 5 -c 1 -o gpurun_out/prof_lattice_c4_${TAG} -f python bench.py --workload c4 --steps 5 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 echo "== ncu full (grad, rowstats c4)"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:"ctc_grad|ctc_row_stats" -s 10 -c 2 -o gpurun_out/prof_dense_c4_${TAG} -f python bench.py --workload c4 --steps 5 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 ls -la gpurun_out | tail -20
