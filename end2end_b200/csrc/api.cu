@@ -162,7 +162,63 @@ static bool make_sweep_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   return true;
 }
 
+// Wave kernel (fused small-alphabet path): variants by (cells per lane, lattice warps per sweep).
+static bool make_wave_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
+  if (!fused || d.dtype == E2E_F64 || d.alphabet > kDenseMaxAlphabet) return false;
+  if (env_int("E2E_CTC_WAVE", 0) == 0 || env_int("E2E_CTC_NO_FUSED", 0) || env_int("E2E_CTC_LEGACY", 0) ||
+      env_int("E2E_CTC_CELLS_PER_LANE", 0) || env_int("E2E_CTC_LATTICE_WARPS", 0)) return false;
+  static const int kVar[][2] = {{4, 1}, {4, 2}, {4, 4}, {4, 8}, {8, 8}};
+  const int S = 2 * d.max_targets + 1;
+  const int fw = env_int("E2E_CTC_WAVE_NW", 0), fk = env_int("E2E_CTC_WAVE_K", 0);
+  int K = 0, NW = 0;
+  for (const auto& v : kVar)
+    if (32 * v[0] * v[1] >= S && (!fw || v[1] == fw) && (!fk || v[0] == fk) && !K) { K = v[0]; NW = v[1]; }
+  if (!K) return false;
+  WaveLayout L;
+  L.K = K; L.NW = NW;
+  L.NC = env_int("E2E_CTC_WAVE_NC", NW >= 4 ? 4 : 2);
+  L.NP = env_int("E2E_CTC_WAVE_NP", NW >= 4 ? 4 : 1);
+  if (L.NC < 1 || L.NC > 4 || L.NP < 1 || L.NP > 4) return false;
+  const int lanes = 32 * NW, roww = lanes * (K + 1);
+  L.es = d.alphabet + 2;
+  L.vpad = (d.alphabet + 3) & ~3;
+  L.RV = env_int("E2E_CTC_WAVE_RV", lanes * K >= 1024 ? 16 : 32);
+  L.R = 64;
+  while (L.R > 16 && (size_t)L.R * L.es * 8 > 48 * 1024) L.R >>= 1;
+  if (L.RV > L.R / 2) L.RV = L.R / 2;
+  if (L.RV < kWaveCF || (L.RV & (L.RV - 1))) return false;
+  size_t off = 0;
+  L.off_lab = 0; off = (size_t)align16i((size_t)(lanes * K / 2 + 1) * 4);
+  L.off_E = (int)off; off = (size_t)align16i(off + (size_t)L.R * L.es * 8);
+  L.off_valw = (int)off; off += (size_t)L.RV * lanes * K * 4;
+  L.off_vale = (int)off; off += (size_t)L.RV * lanes * 4;
+  L.off_stage = (int)off; off += (size_t)L.NC * kWavePF * roww * 4;
+  L.off_acc = (int)off; off += (size_t)L.NC * L.vpad * 4;
+  L.off_bnd = (int)off; off += (size_t)NW * kWaveRB * 16;
+  L.off_ctl = (int)off; off += wave_ctl_bytes();
+  L.total = (int)off;
+  if (off > 220 * 1024) return false;
+  p->wave = 1; p->sweep = 0; p->wv = L;
+  p->K = K; p->NW = NW; p->cells = lanes * K; p->lanes = lanes; p->words = K + 1;
+  p->dense = 1; p->rowlen = d.alphabet; p->vpad = L.vpad;
+  p->lstride = 0; p->np = L.NP; p->nc = L.NC; p->pfd = kWavePF; p->chunk_log2 = 3; p->post_stride = 0;
+  p->smem = off;
+  const size_t rows = (size_t)d.batch * d.max_frames;
+  size_t o = 0;
+  p->off_status = o; o += 256;
+  p->off_meet = o; o += align256((size_t)d.batch * 8);
+  p->off_flags = o; o += align256((size_t)d.batch * 4);
+  p->off_stats = o;
+  p->off_stash = o; o += align256(rows * roww * 4);
+  p->off_post = o;
+  p->total = o;
+  return true;
+}
+
 bool make_loss_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
+  p->wave = 0; p->off_meet = 0;
+  if (make_wave_plan(d, fused, p)) return true;
+  p->wave = 0;
   p->sweep = 0;
   if (env_int("E2E_CTC_LEGACY", 0) == 0 && make_sweep_plan(d, fused, p)) return true;
   p->sweep = 0;
@@ -260,6 +316,10 @@ static int loss_forward(const e2e_ctc_desc& d, const LossPlan& p, const void* lo
 static int loss_fwd_bwd(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
                         const void* in_len, const void* tgt_len, void* losses, void* grads, double scale,
                         char* ws, cudaStream_t s) {
+  if (p.wave) {
+    E2E_CUDA_TRY(cudaMemsetAsync(ws + p.off_status, 0, p.off_flags, s));   // status word + the meet flags
+    return launch_wave(d, p, logits, targets, in_len, tgt_len, losses, grads, scale, ws, s);
+  }
   if (p.dense) {
     E2E_CUDA_TRY(cudaMemsetAsync(ws + p.off_status, 0, 256, s));
     if (p.sweep) return launch_sweep(d, p, logits, targets, in_len, tgt_len, losses, grads, scale, ws, s);

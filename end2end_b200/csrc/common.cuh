@@ -34,8 +34,24 @@ struct SweepLayout {
   int off_lab, off_warp, warp_bytes, w_E, w_raw, w_stat, w_rs, w_acc, w_stage;
 };
 
+constexpr int kWaveCF = 8;       // wave kernel: frames per hand-off chunk
+constexpr int kWaveRB = 32;      // boundary-slot ring depth (frames)
+constexpr int kWavePF = 4;       // stashed rows each combiner warp keeps in flight
+// shared-memory layout and role counts of the wave kernel (ctc_wave_impl.cuh)
+struct WaveLayout {
+  int K, NW;        // cells per lane, lattice warps per sweep
+  int NP, NC;       // producer (row log-softmax) warps, combiner warps
+  int R, RV;        // frames in the emission ring / in the val ring (powers of two)
+  int es;           // doubles per emission-ring frame: V symbols, a zero column, the row normaliser
+  int vpad;         // u32 posterior accumulators per combiner warp
+  int off_lab, off_E, off_valw, off_vale, off_stage, off_acc, off_bnd, off_ctl, total;
+};
+
 // One forward call leaves everything the backward needs in the caller's workspace.
 struct LossPlan {
+  int wave;         // 1: the wave kernel (ctc_wave_*.cu): fused small-alphabet path
+  WaveLayout wv;
+  size_t off_meet;
   int sweep;        // 1: one-warp-per-sweep kernel (ctc_sweep_*.cu); 0: the warp-specialised cluster kernel
   SweepLayout sw;
   int K;            // lattice cells per lane (even: cells alternate blank,label)
@@ -192,6 +208,10 @@ int lattice_trace_read(long long* host, size_t n);
 int launch_sweep(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
                  const void* in_len, const void* tgt_len, void* losses, void* grads, double scale, char* ws,
                  cudaStream_t s);
+int launch_wave(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
+                const void* in_len, const void* tgt_len, void* losses, void* grads, double scale, char* ws,
+                cudaStream_t s);
+size_t wave_ctl_bytes();
 constexpr int kSweepMaxCellsPerLane = 40;   // one warp covers 32 * 40 = 1280 cells: L <= 639
 int launch_scale_rows(const e2e_ctc_desc& d, void* grads, const void* grad_out, int grad_out_count, cudaStream_t s);
 int launch_reduce(const void* losses, int dtype, int B, double scale, void* out, double* out64,

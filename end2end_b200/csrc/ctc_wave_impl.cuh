@@ -1,0 +1,704 @@
+// K2 "wave" kernel -- the whole fused loss path (row log-softmax, alpha/beta lattice, gradient write) for
+// small alphabets, organised so that the per-frame dependent chain carries nothing but the recurrence.
+//
+// Replaces CTCLossEngine::compute_2d (src/losses/ctc_loss.cpp:15-118): extended targets (:25-31),
+// alpha (:33-61), loss (:63-70), beta (:72-100), alpha+beta / gradient (:102-117), plus F.log_softmax
+// (pytorch_end2end/modules/ctc_loss.py:40) and the exp(logits) term of the gradient (:117).
+//
+// Design ("K2w"):
+//  * One 2-CTA cluster per utterance: CTA 0 sweeps alpha forward in time, CTA 1 sweeps beta backward,
+//    concurrently on two SMs.  The beta recursion is the alpha recursion of the REVERSED label sequence
+//    over REVERSED time, so both CTAs run the same code: the backward CTA reverses its labels once and
+//    indexes lattice cell m' = S-1-m.  Each sweep stores its first half of the frames to a global stash
+//    (L2), the two meet once through a global flag, and in its second half each multiplies its own cells
+//    with the other sweep's stashed row: the dependent chain is T frames, not 2T.
+//  * Warp roles inside a CTA, decoupled by shared-memory rings and monotonic progress counters:
+//      producers : fused row log-softmax.  One warp per frame: coalesced row load, warp-shuffle max /
+//                  sum-exp, emissions p(t,v) written as doubles into the E ring, chunks ahead of the sweep.
+//      lattice   : NW warps, K cells per lane (cells alternate blank,label).  The s-1/s-2 transitions
+//                  cross lanes with one 64-bit shuffle; they cross WARPS through a 16-byte self-validating
+//                  shared-memory slot per frame (value + exponent + sequence tag in one vector store), so
+//                  warp w simply runs a frame or more behind warp w-1: a software wavefront with no
+//                  barrier on the recurrence.  Each frame the lanes drop the top 32 bits of their cells
+//                  (+ the lane's block exponent) into the `val` ring and do nothing else.
+//      combiners : drain the val ring, frames round-robin.  First half: copy rows to the global stash.
+//                  Second half: cp.async-prefetch the other sweep's stashed row, multiply, normalise by
+//                  Z = sum_s alpha*beta, sum the posteriors per symbol with integer shared-memory atomics
+//                  (bitwise reproducible) and write the gradient row scale * (softmax - posterior).
+//  * Arithmetic: LINEAR-domain fp64 with a per-lane block exponent (value = x * 2^e).  A cell update is
+//    DADD (+ predicated DADD) + DMUL; the block exponents are re-centred every second frame from a
+//    snapshot of the previous frame, folded into the emission multipliers (ctc_sweep_impl.cuh scheme).
+#pragma once
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace e2e {
+namespace {
+
+struct WaveParams {
+  const void* logits; int dtype; long long sb, st;
+  void* grads; long long gsb, gst; double scale;
+  const void* targets; int tgt_is64; long long ts_b;
+  const void* in_len; const void* tgt_len; int len_is64;
+  int B, T, V, Lmax, blank, from_logits;
+  void* losses;
+  int* status; int* flags; int* meet;
+  uint32_t* stash;     // [B*T][32*NW*(K+1)]: K*lanes cell words, then one exponent per lane
+  long long* dbg;      // E2E_CTC_WAVE_DBG=1: [cta 0/1][warp 16][8] cycle counters of utterance 0 (else NULL)
+  WaveLayout L;
+};
+
+// control block (shared memory, ints)
+struct WaveCtl {
+  volatile int e_ready[4];       // producer pw: chunks pw, pw+NP, ... up to (value-1) are in the E ring
+  volatile int lat_prog[8];      // lattice warp w: frames [0, value) swept and dropped into the val ring
+  volatile int comb_done[4];     // combiner q: the next frame it will take (all its earlier frames are done)
+  int zero;                      // no path survives / NaN input
+  int misc[3];
+  double tail_x[2]; int tail_e[2]; int tail_on[2];
+  double lse[4];
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t wv_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void wv_cp_async_cg16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(wv_smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void wv_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void wv_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint4 wv_ld_volatile_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(wv_smem_u32(p)) : "memory");
+  return r;
+}
+__device__ __forceinline__ void wv_st_volatile_v4(void* p, uint4 v) {
+  asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(wv_smem_u32(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ int wv_ld_acquire_gpu(const int* p) {
+  int r;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ double wv_hi2d(uint32_t h) { return __hiloint2double((int)h, 0); }
+
+// p(t, v) relative to the row's log-sum-exp, as a double: the exponent argument is formed as torch's fp32
+// log_softmax does ((x - max) - logsum, fp32) for raw logits, so the emission equals exp(double(lp32)) of the
+// reference up to one fp32 exp rounding.
+__device__ __noinline__ double wv_emission(float x, float m, float ls, int from_logits) {
+  if (from_logits) return (double)expf((x - m) - ls);
+  const double d = (double)x - ((double)m + (double)ls);
+  const float hi = (float)d;
+  const float lo = (float)(d - (double)hi);
+  return (double)expf(hi) * (1.0 + (double)lo);
+}
+
+struct WaveView {
+  int* lab; double* E; uint32_t* valw; int* vale; uint32_t* stage; uint32_t* acc; uint4* bnd; WaveCtl* ctl;
+};
+__device__ __forceinline__ WaveView wv_carve(unsigned char* base, const WaveLayout& L) {
+  WaveView v;
+  v.lab = reinterpret_cast<int*>(base + L.off_lab);
+  v.E = reinterpret_cast<double*>(base + L.off_E);
+  v.valw = reinterpret_cast<uint32_t*>(base + L.off_valw);
+  v.vale = reinterpret_cast<int*>(base + L.off_vale);
+  v.stage = reinterpret_cast<uint32_t*>(base + L.off_stage);
+  v.acc = reinterpret_cast<uint32_t*>(base + L.off_acc);
+  v.bnd = reinterpret_cast<uint4*>(base + L.off_bnd);
+  v.ctl = reinterpret_cast<WaveCtl*>(base + L.off_ctl);
+  return v;
+}
+
+#define WV_DBG_ADD(slot, val) do { if (dbgp) dbgp[slot] += (val); } while (0)
+#define WV_CLK() (dbgp ? clock64() : 0ll)
+
+template <int N>
+__device__ __forceinline__ int wv_min_prog(const volatile int* a, int n) {
+  int m = a[0];
+#pragma unroll
+  for (int k = 1; k < N; k++) if (k < n) m = min(m, a[k]);
+  return m;
+}
+
+// ---- producers: fused row log-softmax -> E ring ---------------------------------------------------
+// NF frames at a time: all row loads are issued before the first use and the warp reductions of the NF
+// frames are interleaved (offset-major), so a batch costs a few shuffle latencies, not NF times that.
+template <int NQ>
+__device__ __noinline__ double wave_produce_frames(const WaveParams& p, const WaveView& sv, long long xbase, int Ti,
+                                                   int i0, int lane, bool BWD) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int NF = 4;
+  const WaveLayout& L = p.L;
+  const int nf = min(NF, Ti - i0);
+  float xv[NF][NQ];
+  if (p.dtype == E2E_F32) {
+    const float* base = reinterpret_cast<const float*>(p.logits);
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+      const int i = min(i0 + f, Ti - 1);
+      const long long ro = xbase + (long long)(BWD ? (Ti - 1 - i) : i) * p.st;
+#pragma unroll
+      for (int q = 0; q < NQ; q++) {
+        const int v = lane + 32 * q;
+        xv[f][q] = (f < nf && v < p.V) ? __ldg(base + ro + v) : -INFINITY;
+      }
+    }
+  } else {
+    const unsigned short* base = reinterpret_cast<const unsigned short*>(p.logits);
+    unsigned short rw[NF][NQ];
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+      const int i = min(i0 + f, Ti - 1);
+      const long long ro = xbase + (long long)(BWD ? (Ti - 1 - i) : i) * p.st;
+#pragma unroll
+      for (int q = 0; q < NQ; q++) {
+        const int v = lane + 32 * q;
+        rw[f][q] = (f < nf && v < p.V) ? __ldg(base + ro + v) : (unsigned short)0;
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < NF; f++)
+#pragma unroll
+      for (int q = 0; q < NQ; q++) {
+        const int v = lane + 32 * q;
+        const float x = p.dtype == E2E_BF16 ? __uint_as_float((uint32_t)rw[f][q] << 16) : __half2float(__ushort_as_half(rw[f][q]));
+        xv[f][q] = (f < nf && v < p.V) ? x : -INFINITY;
+      }
+  }
+  float m[NF], s[NF];
+  bool nan[NF];
+#pragma unroll
+  for (int f = 0; f < NF; f++) {
+    float mm = xv[f][0];
+    bool nn = xv[f][0] != xv[f][0];
+#pragma unroll
+    for (int q = 1; q < NQ; q++) { mm = fmaxf(mm, xv[f][q]); nn |= xv[f][q] != xv[f][q]; }
+    m[f] = mm; nan[f] = nn;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int f = 0; f < NF; f++) m[f] = fmaxf(m[f], __shfl_xor_sync(FULL, m[f], o));
+#pragma unroll
+  for (int f = 0; f < NF; f++) {
+    nan[f] = __any_sync(FULL, nan[f]);
+    float ss = 0.f;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) ss += expf(xv[f][q] - m[f]);   // exp(-inf) = 0 for the padding lanes
+    s[f] = ss;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int f = 0; f < NF; f++) s[f] += __shfl_xor_sync(FULL, s[f], o);
+  double lse = 0.0;
+#pragma unroll
+  for (int f = 0; f < NF; f++) {
+    if (f < nf) {
+      float mf = m[f], ls = logf(s[f]);
+      if (nan[f]) { mf = NAN; ls = NAN; }
+      double* Erow = sv.E + (size_t)((i0 + f) & (L.R - 1)) * L.es;
+#pragma unroll
+      for (int q = 0; q < NQ; q++) {
+        const int v = lane + 32 * q;
+        if (v < p.V) Erow[v] = wv_emission(xv[f][q], mf, ls, p.from_logits);
+      }
+      if (lane == 0) {
+        const double mls = (double)mf + (double)ls;
+        Erow[p.V] = 0.0;                                       // the column padding cells read
+        Erow[p.V + 1] = p.from_logits ? 1.0 : exp(mls);        // turns the emission back into exp(x)
+        lse += mls;
+      }
+    }
+  }
+  return lse;
+}
+
+template <int NW>
+__device__ void wave_producer(const WaveParams& p, const WaveView& sv, int b, int Ti, int pw, int lane, bool BWD, long long* dbgp) {
+  const long long tstart = WV_CLK();
+  constexpr int CF = kWaveCF;
+  const WaveLayout& L = p.L;
+  const int nchunks = (Ti + CF - 1) / CF;
+  const long long xbase = (long long)b * p.sb;
+  const int nq = (p.V + 31) >> 5;
+  double lse = 0.0;
+  for (int c = pw; c < nchunks; c += L.NP) {
+    const int need = c * CF + CF - L.R;   // frames below `need` must have left the ring
+    if (need > 0) {
+      const long long t0 = WV_CLK();
+      while (wv_min_prog<8>(sv.ctl->lat_prog, NW) < need || wv_min_prog<4>(sv.ctl->comb_done, L.NC) < need) __nanosleep(64);
+      __threadfence_block();
+      WV_DBG_ADD(1, WV_CLK() - t0);
+    }
+#pragma unroll 1
+    for (int i0 = c * CF; i0 < min(c * CF + CF, Ti); i0 += 4) {
+      if (nq == 1) lse += wave_produce_frames<1>(p, sv, xbase, Ti, i0, lane, BWD);
+      else lse += wave_produce_frames<4>(p, sv, xbase, Ti, i0, lane, BWD);
+    }
+    __syncwarp();
+    if (lane == 0) { __threadfence_block(); sv.ctl->e_ready[pw] = c + 1; }
+  }
+  if (lane == 0) sv.ctl->lse[pw] = lse;
+  WV_DBG_ADD(0, WV_CLK() - tstart);
+}
+
+// ---- lattice warps ----------------------------------------------------------------------------------
+template <int K, int NW>
+__device__ void wave_lattice(const WaveParams& p, const WaveView& sv, int b, int Ti, int Li, int w, int lane, bool BWD, long long* dbgp) {
+  const long long tstart = WV_CLK();
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int H = K / 2, LANES = 32 * NW, CF = kWaveCF, RB = kWaveRB;
+  const WaveLayout& L = p.L;
+  const int S = 2 * Li + 1;
+  const int g = w * 32 + lane;
+  const int m0 = g * K;
+
+  int ecol[H];
+  unsigned skipm = 0;
+#pragma unroll
+  for (int h = 0; h < H; h++) {
+    const int li = g * H + h;
+    const bool lv = li < Li;
+    const int lab = sv.lab[li];        // padded with blank past L_i
+    ecol[h] = lv ? lab : p.V;          // the zero column
+    const bool sk = lv && li >= 1 && lab != p.blank && lab != sv.lab[li - 1];
+    skipm |= sk ? (1u << h) : 0u;
+  }
+  const int bcol = p.blank;
+
+  double x[K];
+#pragma unroll
+  for (int j = 0; j < K; j++) x[j] = (m0 + j == 0) ? 1.0 : 0.0;   // a virtual frame before the first: all mass on cell 0
+  int e = 0;
+  double fb = lane == 0 ? 0.0 : 1.0;
+  int en_next = 0;
+  double f_next = 1.0, fb_next = fb;
+  int src_e = 0;                       // lane 0 of warps > 0: exponent of the last boundary value received
+  uint4* const bnd_in = sv.bnd + (size_t)(w > 0 ? w - 1 : 0) * RB;
+  uint4* const bnd_out = sv.bnd + (size_t)w * RB;
+
+  for (int i = 0; i < Ti; ++i) {
+    if ((i & (CF - 1)) == 0) {
+      const int c = i / CF;
+      const long long t0 = WV_CLK();
+      const volatile int* er = &sv.ctl->e_ready[c % L.NP];
+      while (*er <= c) {}
+      const long long t1 = WV_CLK();
+      const int needv = i + CF - L.RV;
+      if (needv > 0) { while (wv_min_prog<4>(sv.ctl->comb_done, L.NC) < needv) {} }
+      const long long t2 = WV_CLK();
+      if (NW > 1 && w + 1 < NW) {
+        const int needb = i + CF - RB + 1;   // the slots this chunk overwrites have been read
+        if (needb > 0) { while (sv.ctl->lat_prog[w + 1] < needb) {} }
+      }
+      __threadfence_block();
+      WV_DBG_ADD(1, t1 - t0); WV_DBG_ADD(2, t2 - t1); WV_DBG_ADD(3, WV_CLK() - t2);
+    }
+    const double* Erow = sv.E + (size_t)(i & (L.R - 1)) * L.es;
+    double mulb = Erow[bcol];
+    double mull[H];
+#pragma unroll
+    for (int h = 0; h < H; h++) mull[h] = Erow[ecol[h]];
+    const bool snap = (i & 1) == 0, apply = !snap;
+
+    // boundary cell from the previous lane / the previous warp
+    double bxs = __shfl_up_sync(FULL, x[K - 1], 1) * fb;
+    if (NW > 1 && w > 0) {
+      if (i > 0) {
+        const uint4* slot = bnd_in + ((i - 1) & (RB - 1));
+        uint4 q;
+        const long long t0 = WV_CLK();
+        do { q = wv_ld_volatile_v4(slot); } while ((int)q.w != i);
+        WV_DBG_ADD(4, WV_CLK() - t0);
+        if (lane == 0) {
+          src_e = (int)q.z;
+          bxs = __hiloint2double((int)q.y, (int)q.x) * pow2i(src_e - e);
+        }
+      }
+    }
+
+    if (snap) {
+      // where the lane's scale should move (applied next frame): block maximum into [1,2)
+      int mhi = 0;
+#pragma unroll
+      for (int j = 0; j < K; j++) mhi = max(mhi, __double2hiint(x[j]));
+      int nb_e = __shfl_up_sync(FULL, e, 1);
+      if (lane == 0) nb_e = (NW > 1 && w > 0) ? src_e : e;
+      const int en = mhi == 0 ? nb_e : e + ((mhi >> 20) - 1023);   // an all-zero lane follows the lane its mass will come from
+      const int nb_en = __shfl_up_sync(FULL, en, 1);
+      en_next = en;
+      f_next = pow2i(e - en);
+      fb_next = lane == 0 ? 0.0 : pow2i(nb_en - en);
+    }
+    if (apply) {
+      mulb *= f_next;
+#pragma unroll
+      for (int h = 0; h < H; h++) mull[h] *= f_next;
+    }
+    // cell j gathers j, j-1 and (label cells, when allowed) j-2 of the previous frame; in place, top down
+    double so[K];
+#pragma unroll
+    for (int j = K - 1; j >= 2; j--) {
+      double a = x[j] + x[j - 1];
+      if ((j & 1) && (skipm & (1u << (j >> 1)))) a += x[j - 2];
+      so[j] = a;
+      x[j] = a * ((j & 1) ? mull[j >> 1] : mulb);
+    }
+    {
+      double a = x[1] + x[0];
+      if (skipm & 1u) a += bxs;
+      so[1] = a;
+      x[1] = a * mull[0];
+      so[0] = x[0] + bxs;
+      x[0] = so[0] * mulb;
+    }
+    // drop the frame into the val ring: alpha with its emission (forward), beta before its emission (backward)
+    {
+      const size_t ent = (size_t)(i & (L.RV - 1)) * LANES + g;
+      uint32_t wd[K];
+#pragma unroll
+      for (int j = 0; j < K; j++) wd[j] = (uint32_t)(BWD ? __double2hiint(so[j]) : __double2hiint(x[j]));
+#pragma unroll
+      for (int u = 0; u < K / 4; u++)
+        reinterpret_cast<uint4*>(sv.valw + ent * K)[u] = make_uint4(wd[4 * u], wd[4 * u + 1], wd[4 * u + 2], wd[4 * u + 3]);
+      sv.vale[ent] = BWD ? e : (apply ? en_next : e);
+    }
+    if (apply) { e = en_next; fb = fb_next; }
+    if (NW > 1 && w + 1 < NW && lane == 31)
+      wv_st_volatile_v4(bnd_out + (i & (RB - 1)),
+                        make_uint4((uint32_t)__double2loint(x[K - 1]), (uint32_t)__double2hiint(x[K - 1]), (uint32_t)e, (uint32_t)(i + 1)));
+    if ((i & (CF - 1)) == CF - 1 || i == Ti - 1) {
+      __syncwarp();
+      if (lane == 0) { __threadfence_block(); sv.ctl->lat_prog[w] = i + 1; }
+    }
+  }
+  WV_DBG_ADD(0, WV_CLK() - tstart);
+  // exit cells S-1 and S-2 of the last frame: Z = their sum (ctc_loss.cpp:63-70)
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    const int m = m0 + j;
+    if (m == S - 1) { sv.ctl->tail_x[0] = x[j]; sv.ctl->tail_e[0] = e; sv.ctl->tail_on[0] = 1; }
+    if (m == S - 2) { sv.ctl->tail_x[1] = x[j]; sv.ctl->tail_e[1] = e; sv.ctl->tail_on[1] = 1; }
+  }
+}
+
+// ---- combiner warps ---------------------------------------------------------------------------------
+// The K cells of lattice lane g in one frame, multiplied with the same cells of the other sweep's stored row:
+// pr[j] = (my cell) * (other cell) as a double of the two 32-bit tops, El[j] = sum of the two block exponents.
+template <int K>
+__device__ __forceinline__ void wave_pair_cells(const uint32_t* valw_row, const int* vale_row, const uint32_t* orow, int cells,
+                                                int S, int g, double (&pr)[K], int (&El)[K]) {
+  constexpr int KLOG = K == 4 ? 2 : 3;
+  uint32_t wd[K];
+#pragma unroll
+  for (int v = 0; v < K / 4; v++) {
+    const uint4 t4 = reinterpret_cast<const uint4*>(valw_row + (size_t)g * K)[v];
+    wd[4 * v] = t4.x; wd[4 * v + 1] = t4.y; wd[4 * v + 2] = t4.z; wd[4 * v + 3] = t4.w;
+  }
+  const int em = vale_row[g];
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    const int mp = S - 1 - (g * K + j);          // the same lattice cell in the other sweep's indexing
+    const bool valid = mp >= 0;
+    const int mpc = valid ? mp : 0;
+    const uint32_t ow = orow[mpc];
+    const int oe = (int)orow[cells + (mpc >> KLOG)];
+    pr[j] = valid ? wv_hi2d(wd[j]) * wv_hi2d(ow) : 0.0;
+    El[j] = em + oe;
+  }
+}
+
+template <int K, int NW>
+__device__ void wave_combiner(const WaveParams& p, const WaveView& sv, int b, int Ti, int Li, int q, int lane, bool BWD, long long* dbgp) {
+  const long long tstart = WV_CLK();
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int LANES = 32 * NW, CELLS = LANES * K, ROWW = LANES * (K + 1), PF = kWavePF;
+  const WaveLayout& L = p.L;
+  const int NC = L.NC;
+  const int S = 2 * Li + 1;
+  const int tm = Ti / 2;
+  const int nstore = BWD ? (Ti - tm) : tm;          // frames this sweep stores; the rest it combines
+  const int nstore_peer = Ti - nstore;
+  auto frame_t = [&](int i) { return BWD ? (Ti - 1 - i) : i; };
+  uint32_t* const stash_b = p.stash + (size_t)b * p.T * ROWW;
+  uint32_t* const stage = sv.stage + (size_t)q * PF * ROWW;
+  uint32_t* const acc = sv.acc + (size_t)q * L.vpad;
+
+  auto wait_val = [&](int i) {
+    const long long t0 = WV_CLK();
+    while (wv_min_prog<8>(sv.ctl->lat_prog, NW) <= i) __nanosleep(32);
+    __threadfence_block();
+    WV_DBG_ADD(1, WV_CLK() - t0);
+  };
+  auto done = [&](int i) {
+    __syncwarp();
+    if (lane == 0) { __threadfence_block(); sv.ctl->comb_done[q] = i + NC; }
+  };
+  auto prefetch = [&](int i2, int slot) {   // the other sweep's stored row of my frame i2 -> staging slot
+    if (i2 < Ti) {
+      uint32_t* dst = stage + (size_t)slot * ROWW;
+      const uint32_t* src = stash_b + (size_t)frame_t(i2) * ROWW;
+      for (int u = lane; u < ROWW / 4; u += 32) wv_cp_async_cg16(dst + 4 * u, src + 4 * u);
+    }
+  };
+
+  int i = q;
+  // ---- first half: val ring -> global stash ----
+  for (; i < nstore; i += NC) {
+    wait_val(i);
+    const size_t ent0 = (size_t)(i & (L.RV - 1)) * LANES;
+    uint32_t* row = stash_b + (size_t)frame_t(i) * ROWW;
+#pragma unroll
+    for (int u = 0; u < NW; u++) {
+      const int g = lane + 32 * u;
+#pragma unroll
+      for (int v = 0; v < K / 4; v++)
+        reinterpret_cast<uint4*>(row + (size_t)g * K)[v] = reinterpret_cast<const uint4*>(sv.valw + (ent0 + g) * K)[v];
+      row[CELLS + g] = (uint32_t)sv.vale[ent0 + g];
+    }
+    if (i + NC >= nstore) {   // my last stored row: publish to the other CTA
+      __syncwarp();
+      if (lane == 0) { __threadfence(); atomicAdd(p.meet + 2 * b + (BWD ? 1 : 0), 1); }
+    }
+    done(i);
+  }
+  WV_DBG_ADD(2, WV_CLK() - tstart);
+  if (i >= Ti) return;
+  const long long tmeet = WV_CLK();
+  // ---- meet: the other sweep's stored rows must be visible ----
+  {
+    const int want = min(NC, nstore_peer);
+    const int* flag = p.meet + 2 * b + (BWD ? 0 : 1);
+    while (wv_ld_acquire_gpu(flag) < want) __nanosleep(64);
+  }
+  WV_DBG_ADD(4, WV_CLK() - tmeet);
+  const long long tsecond = WV_CLK();
+  for (int u = 0; u < PF; u++) { prefetch(i + u * NC, u); wv_cp_async_commit(); }
+
+  bool have_z = false;
+  double cz = 0.0;   // 2^31 / Z
+  int Ez = 0;
+  const float sc = (float)p.scale;
+  for (int k = 0; i < Ti; i += NC, ++k) {
+    wait_val(i);
+    { const long long t0 = WV_CLK(); wv_cp_async_wait<PF - 1>(); __syncwarp(); WV_DBG_ADD(5, WV_CLK() - t0); }
+    const uint32_t* orow = stage + (size_t)(k % PF) * ROWW;
+    const size_t ent0 = (size_t)(i & (L.RV - 1)) * LANES;
+    const uint32_t* valw_row = sv.valw + ent0 * K;
+    const int* vale_row = sv.vale + ent0;
+    if (!have_z) {
+      // Z = sum_s alpha(t,s) * beta(t,s), the same for every frame: taken once per combiner warp
+      int emax = 4 * kNegExp;
+#pragma unroll 1
+      for (int u = 0; u < NW; u++) {
+        double pr[K]; int El[K];
+        wave_pair_cells<K>(valw_row, vale_row, orow, CELLS, S, lane + 32 * u, pr, El);
+#pragma unroll
+        for (int j = 0; j < K; j++) if (pr[j] > 0.0) emax = max(emax, El[j]);
+      }
+      emax = warp_max_int(emax);
+      double tot = 0.0;
+#pragma unroll 1
+      for (int u = 0; u < NW; u++) {
+        double pr[K]; int El[K];
+        wave_pair_cells<K>(valw_row, vale_row, orow, CELLS, S, lane + 32 * u, pr, El);
+#pragma unroll
+        for (int j = 0; j < K; j++) if (pr[j] > 0.0) tot += pr[j] * pow2i(El[j] - emax);
+      }
+      tot = warp_sum(tot);
+      cz = 2147483648.0 / tot;   // tot == 0: the lattice tail flags the utterance and the block is overwritten with NaN
+      Ez = emax;
+      have_z = true;
+    }
+    // posteriors summed per symbol: fixed point 2^-31 (the sum per symbol is <= 1), integer adds commute
+    uint32_t bsum = 0u;
+#pragma unroll 1
+    for (int u = 0; u < NW; u++) {
+      const int g = lane + 32 * u;
+      double pr[K]; int El[K];
+      wave_pair_cells<K>(valw_row, vale_row, orow, CELLS, S, g, pr, El);
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        // lanes the mass has not reached carry stale block exponents: their scale may overflow (0 * inf);
+        // anything that is not a posterior (<= 1, i.e. <= 2^31 here) counts as zero
+        const double pv = pr[j] * (pow2i(El[j] - Ez) * cz);
+        const uint32_t qv = pv < 2149580800.0 ? __double2uint_rn(pv) : 0u;
+        if (j & 1) {
+          const int li = (g * K + j) >> 1;
+          if (li < Li) atomicAdd(acc + sv.lab[li], qv);
+        } else {
+          bsum += qv;
+        }
+      }
+    }
+    const uint32_t qb = __reduce_add_sync(FULL, bsum);
+    __syncwarp();
+    // gradient row: scale * (softmax - posterior); log-prob input: exp(lp) - posterior (the engine contract)
+    {
+      const int t = frame_t(i);
+      const double* Erow = sv.E + (size_t)(i & (L.R - 1)) * L.es;
+      const float rs = (float)Erow[p.V + 1];
+      const long long gbase = (long long)b * p.gsb + (long long)t * p.gst;
+      for (int v = lane; v < p.V; v += 32) {
+        const uint32_t a = acc[v] + (v == p.blank ? qb : 0u);
+        acc[v] = 0u;
+        const float gv = sc * ((float)Erow[v] * rs - (float)a * (1.f / 2147483648.f));
+        if (p.dtype == E2E_F32) reinterpret_cast<float*>(p.grads)[gbase + v] = gv;
+        else if (p.dtype == E2E_BF16) reinterpret_cast<__nv_bfloat16*>(p.grads)[gbase + v] = __float2bfloat16_rn(gv);
+        else reinterpret_cast<__half*>(p.grads)[gbase + v] = __float2half_rn(gv);
+      }
+    }
+    __syncwarp();
+    prefetch(i + PF * NC, k % PF);
+    wv_cp_async_commit();
+    done(i);
+  }
+  wv_cp_async_wait<0>();
+  WV_DBG_ADD(3, WV_CLK() - tsecond);
+  WV_DBG_ADD(0, WV_CLK() - tstart);
+}
+
+// ---- kernel -------------------------------------------------------------------------------------------
+template <int K, int NW>
+__device__ void wave_roles(const WaveParams& p, const WaveView& sv, int b, int Ti, int Li, int w, int lane, bool BWD) {
+  const WaveLayout& L = p.L;
+  long long* dbgp = (p.dbg != nullptr && b == 0 && lane == 0 && w < 16) ? p.dbg + ((BWD ? 16 : 0) + w) * 8 : nullptr;
+  const int first_comb = L.NP, first_lat = L.NP + L.NC;
+  if (w >= first_lat) {
+    wave_lattice<K, NW>(p, sv, b, Ti, Li, w - first_lat, lane, BWD, dbgp);
+  } else if (w >= first_comb) {
+    wave_combiner<K, NW>(p, sv, b, Ti, Li, w - first_comb, lane, BWD, dbgp);
+  } else {
+    wave_producer<NW>(p, sv, b, Ti, w, lane, BWD, dbgp);
+    // padding frames t >= T_i: exp(lp) for log-prob input (the engine contract, ctc_loss.cpp:105-117),
+    // 0 for fused-logits input (what the reference's log_softmax backward leaves there)
+    for (int r = Ti + (BWD ? 1 : 0) + 2 * w; r < p.T; r += 2 * L.NP) {
+      const long long xo = (long long)b * p.sb + (long long)r * p.st;
+      const long long go = (long long)b * p.gsb + (long long)r * p.gst;
+      for (int v = lane; v < p.V; v += 32) {
+        double gq = 0.0;
+        if (!p.from_logits) gq = (double)expf(load_as_float(p.logits, p.dtype, xo + v));
+        store_from_double(p.grads, p.dtype, go + v, p.scale * gq);
+      }
+    }
+  }
+}
+
+template <int K, int NW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (NW + 8), 1)
+ctc_wave_kernel(const WaveParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int H = K / 2, LANES = 32 * NW;
+  const WaveView sv = wv_carve(smem_raw, p.L);
+  __shared__ int pre[4];
+
+  const int b = blockIdx.x >> 1;
+  const bool bwd = (blockIdx.x & 1) != 0;
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int nwarps = blockDim.x >> 5;
+
+  const long long Ti_ll = load_index(p.in_len, p.len_is64, b);
+  const long long Li_ll = load_index(p.tgt_len, p.len_is64, b);
+  int bad = 0;
+  if (Ti_ll < 1 || Ti_ll > p.T) bad |= kBadFrames;
+  if (Li_ll < 0 || Li_ll > p.Lmax) bad |= kBadTargetLen;
+  const int Ti = (int)Ti_ll, Li = bad ? 0 : (int)Li_ll;
+  if (tid < 4) pre[tid] = 0;
+  __syncthreads();
+  int rep = 0, badlab = 0;
+  // the backward CTA sweeps the reversed label sequence
+  for (int i = tid; i < Li; i += blockDim.x) {
+    const long long v = load_index(p.targets, p.tgt_is64, (long long)b * p.ts_b + i);
+    if (v < 0 || v >= p.V) badlab = kBadLabel;
+    sv.lab[bwd ? (Li - 1 - i) : i] = (int)v;
+  }
+  for (int i = Li + tid; i < LANES * H + 1; i += blockDim.x) sv.lab[i] = p.blank;   // cells past the lattice carry zero mass
+  __syncthreads();
+  for (int i = tid + 1; i < Li; i += blockDim.x) rep += (sv.lab[i] == sv.lab[i - 1]);
+  if (rep) atomicAdd(&pre[1], rep);
+  if (badlab) atomicOr(&pre[0], badlab);
+  __syncthreads();
+  bad |= pre[0];
+  rep = pre[1];
+  const long long gfill_base = (long long)b * p.gsb;
+  if (bad || Ti < Li + rep) {
+    // out-of-range lengths / labels (undefined behaviour in the reference): NaN loss + status bits;
+    // no alignment exists (T < L + repeats): loss = +inf.  Either way the gradient block is all NaN
+    // (-inf - (-inf) in the reference, ctc_loss.cpp:116-117), padding rows included.
+    if (tid == 0 && !bwd) {
+      if (bad) atomicOr(p.status, bad);
+      p.flags[b] = bad ? kFlagInvalid : kFlagInfeasible;
+      store_from_double(p.losses, p.dtype, b, bad ? (double)NAN : (double)INFINITY);
+    }
+    for (int r = 2 * w + (bwd ? 1 : 0); r < p.T; r += 2 * nwarps)
+      for (int v = lane; v < p.V; v += 32) store_from_double(p.grads, p.dtype, gfill_base + (long long)r * p.gst + v, (double)NAN);
+    return;
+  }
+  {  // control block, accumulators and boundary slots start at zero
+    uint32_t* z = reinterpret_cast<uint32_t*>(smem_raw + p.L.off_acc);
+    const int n = (p.L.total - p.L.off_acc) >> 2;
+    for (int k = tid; k < n; k += blockDim.x) z[k] = 0u;
+  }
+  __syncthreads();
+  if (tid < p.L.NC) sv.ctl->comb_done[tid] = tid;
+  __syncthreads();
+
+  wave_roles<K, NW>(p, sv, b, Ti, Li, w, lane, bwd);
+  __syncthreads();
+
+  // loss = -log(alpha[S-1][T-1] + alpha[S-2][T-1]) (ctc_loss.cpp:63-70) from the live fp64 state of the
+  // forward sweep (the backward sweep's exit cells give the same Z: it only needs the zero test).
+  // Emissions were normalised per row, so for log-prob input the row normalisers are added back.
+  if (tid == 0) {
+    WaveCtl* c = sv.ctl;
+    const double x0 = c->tail_on[0] ? c->tail_x[0] : 0.0, x1 = c->tail_on[1] ? c->tail_x[1] : 0.0;
+    const int e0 = (c->tail_on[0] && x0 > 0.0) ? c->tail_e[0] : 4 * kNegExp;
+    const int e1 = (c->tail_on[1] && x1 > 0.0) ? c->tail_e[1] : 4 * kNegExp;
+    const int emax = max(e0, e1);
+    double z = 0.0;
+    if (x0 > 0.0) z += x0 * pow2i(e0 - emax);
+    if (x1 > 0.0) z += x1 * pow2i(e1 - emax);
+    if (x0 != x0 || x1 != x1) z = NAN;
+    double loss = INFINITY;
+    if (z > 0.0) {
+      loss = -(log(z) + (double)emax * 0.69314718055994530942);
+      if (!p.from_logits) { for (int k = 0; k < p.L.NP; k++) loss -= c->lse[k]; }
+    } else {   // no path survives (exact-zero emissions): +inf; NaN input: NaN.  NaN gradient block either way
+      if (z != z) loss = NAN;
+      c->zero = 1;
+    }
+    if (!bwd) {
+      p.flags[b] = z > 0.0 ? 0 : kFlagInfeasible;
+      store_from_double(p.losses, p.dtype, b, loss);
+    }
+  }
+  __syncthreads();
+  if (sv.ctl->zero) {
+    // each CTA overwrites the rows it wrote: its combined frames and its share of the padding rows
+    const int tm = Ti / 2;
+    for (int r = w; r < p.T; r += nwarps) {
+      const bool mine = r < Ti ? (bwd ? r < tm : r >= tm) : (((r - Ti) & 1) == (bwd ? 1 : 0));
+      if (!mine) continue;
+      for (int v = lane; v < p.V; v += 32) store_from_double(p.grads, p.dtype, gfill_base + (long long)r * p.gst + v, (double)NAN);
+    }
+  }
+}
+
+template <int K, int NW>
+int launch_wave_k(const WaveParams& wp, cudaStream_t s) {
+  static int attr_smem = -1;   // the attribute only ever grows
+  if (wp.L.total > attr_smem) {
+    E2E_CUDA_TRY(cudaFuncSetAttribute(ctc_wave_kernel<K, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, wp.L.total));
+    attr_smem = wp.L.total;
+  }
+  const unsigned threads = 32u * (unsigned)(NW + wp.L.NC + wp.L.NP);
+  KernelTimer timer(kKernelLattice, s);
+  ctc_wave_kernel<K, NW><<<2u * (unsigned)wp.B, threads, (size_t)wp.L.total, s>>>(wp);
+  E2E_CUDA_TRY(cudaGetLastError());
+  return E2E_OK;
+}
+
+}  // namespace
+}  // namespace e2e
