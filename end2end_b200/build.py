@@ -48,7 +48,7 @@ def build(force=False, verbose=False, extra=()):
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJDIR, src.replace(".cu", ".o"))
         if force or _stale(o, [s] + headers):
-            jobs.append([nvcc, *ARCH, *FLAGS, *extra, "-c", s, "-o", o])
+            jobs.append([nvcc, *ARCH, *FLAGS, *extra, *os.environ.get("E2E_BUILD_EXTRA", "").split(), "-c", s, "-o", o])
 
     def run(cmd):
         if verbose:

@@ -176,9 +176,18 @@ static bool make_wave_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   if (!K) return false;
   WaveLayout L;
   L.K = K; L.NW = NW;
-  L.NC = env_int("E2E_CTC_WAVE_NC", NW >= 4 ? 4 : 2);
+  L.NC = env_int("E2E_CTC_WAVE_NC", NW >= 4 ? 8 : 2);
   L.NP = env_int("E2E_CTC_WAVE_NP", NW >= 4 ? 4 : 1);
-  if (L.NC < 1 || L.NC > 4 || L.NP < 1 || L.NP > 4) return false;
+  if (L.NC < 1 || L.NC > 8 || (L.NP != 1 && L.NP != 2 && L.NP != 4)) return false;
+  L.by_smsp = env_int("E2E_CTC_WAVE_BY_SMSP", NW >= 4 ? 1 : 0);
+  if (L.by_smsp) {
+    int r = NW > L.NP ? NW : L.NP;
+    if ((L.NC + 1) / 2 > r) r = (L.NC + 1) / 2;
+    L.nwarps = 4 * r;
+  } else {
+    L.nwarps = NW + L.NC + L.NP;
+  }
+  if (L.nwarps > (NW <= 4 ? 16 : 32)) return false;
   const int lanes = 32 * NW, roww = lanes * (K + 1);
   L.es = d.alphabet + 2;
   L.vpad = (d.alphabet + 3) & ~3;

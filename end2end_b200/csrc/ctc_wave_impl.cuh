@@ -53,7 +53,7 @@ struct WaveParams {
 struct WaveCtl {
   volatile int e_ready[4];       // producer pw: chunks pw, pw+NP, ... up to (value-1) are in the E ring
   volatile int lat_prog[8];      // lattice warp w: frames [0, value) swept and dropped into the val ring
-  volatile int comb_done[4];     // combiner q: the next frame it will take (all its earlier frames are done)
+  volatile int comb_done[8];     // combiner q: the next frame it will take (all its earlier frames are done)
   int zero;                      // no path survives / NaN input
   int misc[3];
   double tail_x[2]; int tail_e[2]; int tail_on[2];
@@ -70,11 +70,12 @@ template <int N>
 __device__ __forceinline__ void wv_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ uint4 wv_ld_volatile_v4(const void* p) {
   uint4 r;
-  asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(wv_smem_u32(p)) : "memory");
+  // no "memory" clobber: the slot is self-validating (sequence tag inside the 16 bytes), nothing else is ordered by it
+  asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(wv_smem_u32(p)));
   return r;
 }
 __device__ __forceinline__ void wv_st_volatile_v4(void* p, uint4 v) {
-  asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(wv_smem_u32(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(wv_smem_u32(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
 __device__ __forceinline__ int wv_ld_acquire_gpu(const int* p) {
   int r;
@@ -110,8 +111,13 @@ __device__ __forceinline__ WaveView wv_carve(unsigned char* base, const WaveLayo
   return v;
 }
 
+#ifdef E2E_WAVE_DBG
 #define WV_DBG_ADD(slot, val) do { if (dbgp) dbgp[slot] += (val); } while (0)
 #define WV_CLK() (dbgp ? clock64() : 0ll)
+#else
+#define WV_DBG_ADD(slot, val) do { (void)dbgp; } while (0)
+#define WV_CLK() (0ll)
+#endif
 
 template <int N>
 __device__ __forceinline__ int wv_min_prog(const volatile int* a, int n) {
@@ -228,7 +234,7 @@ __device__ void wave_producer(const WaveParams& p, const WaveView& sv, int b, in
     const int need = c * CF + CF - L.R;   // frames below `need` must have left the ring
     if (need > 0) {
       const long long t0 = WV_CLK();
-      while (wv_min_prog<8>(sv.ctl->lat_prog, NW) < need || wv_min_prog<4>(sv.ctl->comb_done, L.NC) < need) __nanosleep(64);
+      while (wv_min_prog<8>(sv.ctl->lat_prog, NW) < need || wv_min_prog<8>(sv.ctl->comb_done, L.NC) < need) __nanosleep(64);
       __threadfence_block();
       WV_DBG_ADD(1, WV_CLK() - t0);
     }
@@ -245,18 +251,23 @@ __device__ void wave_producer(const WaveParams& p, const WaveView& sv, int b, in
 }
 
 // ---- lattice warps ----------------------------------------------------------------------------------
-template <int K, int NW>
-__device__ void wave_lattice(const WaveParams& p, const WaveView& sv, int b, int Ti, int Li, int w, int lane, bool BWD, long long* dbgp) {
+// Frames are swept in groups of four (two groups per hand-off chunk) with the group fully unrolled: the
+// block exponents are re-centred once per group (snapshot at the third frame, folded into the emission
+// multipliers of the next group's first frame), so a frame is the recurrence, one shuffle, one boundary
+// slot and two shared-memory stores.  Four frames shrink a cell by at most 2^-600 (fp32 emissions are
+// >= 2^-149), well inside the fp64 range below the re-centred block maximum.
+template <int K, int NW, bool BWD>
+__device__ void wave_lattice(const WaveParams& p, const WaveView& sv, int b, int Ti, int Li, int w, int lane, long long* dbgp) {
   const long long tstart = WV_CLK();
   constexpr unsigned FULL = 0xffffffffu;
-  constexpr int H = K / 2, LANES = 32 * NW, CF = kWaveCF, RB = kWaveRB;
+  constexpr int H = K / 2, LANES = 32 * NW, CF = kWaveCF, RB = kWaveRB, G = 4;
   const WaveLayout& L = p.L;
   const int S = 2 * Li + 1;
   const int g = w * 32 + lane;
   const int m0 = g * K;
 
   int ecol[H];
-  unsigned skipm = 0;
+  double skipd[H];   // 1.0 where the label cell may also gather from s-2 (a different, non-blank label), else 0.0
 #pragma unroll
   for (int h = 0; h < H; h++) {
     const int li = g * H + h;
@@ -264,7 +275,7 @@ __device__ void wave_lattice(const WaveParams& p, const WaveView& sv, int b, int
     const int lab = sv.lab[li];        // padded with blank past L_i
     ecol[h] = lv ? lab : p.V;          // the zero column
     const bool sk = lv && li >= 1 && lab != p.blank && lab != sv.lab[li - 1];
-    skipm |= sk ? (1u << h) : 0u;
+    skipd[h] = sk ? 1.0 : 0.0;
   }
   const int bcol = p.blank;
 
@@ -275,103 +286,119 @@ __device__ void wave_lattice(const WaveParams& p, const WaveView& sv, int b, int
   double fb = lane == 0 ? 0.0 : 1.0;
   int en_next = 0;
   double f_next = 1.0, fb_next = fb;
-  int src_e = 0;                       // lane 0 of warps > 0: exponent of the last boundary value received
-  uint4* const bnd_in = sv.bnd + (size_t)(w > 0 ? w - 1 : 0) * RB;
+  bool pending = false;
+  int src_e = 0, fin_e = 0;            // boundary from the previous warp: its exponent, and my exponent `fin` was built for
+  double fin = 1.0;                    // 2^(src_e - fin_e)
+  const bool has_in = NW > 1 && w > 0, has_out = NW > 1 && w + 1 < NW;
+  const uint4* const bnd_in = sv.bnd + (size_t)(w > 0 ? w - 1 : 0) * RB;
   uint4* const bnd_out = sv.bnd + (size_t)w * RB;
 
-  for (int i = 0; i < Ti; ++i) {
-    if ((i & (CF - 1)) == 0) {
-      const int c = i / CF;
+  for (int i0 = 0; i0 < Ti; i0 += G) {
+    if ((i0 & (CF - 1)) == 0) {
+      const int c = i0 / CF;
       const long long t0 = WV_CLK();
-      const volatile int* er = &sv.ctl->e_ready[c % L.NP];
+      const volatile int* er = &sv.ctl->e_ready[c & (L.NP - 1)];
       while (*er <= c) {}
       const long long t1 = WV_CLK();
-      const int needv = i + CF - L.RV;
-      if (needv > 0) { while (wv_min_prog<4>(sv.ctl->comb_done, L.NC) < needv) {} }
+      const int needv = i0 + CF - L.RV;
+      if (needv > 0) { while (wv_min_prog<8>(sv.ctl->comb_done, L.NC) < needv) {} }
       const long long t2 = WV_CLK();
-      if (NW > 1 && w + 1 < NW) {
-        const int needb = i + CF - RB + 1;   // the slots this chunk overwrites have been read
+      if (has_out) {
+        const int needb = i0 + CF - RB + 1;   // the slots this chunk overwrites have been read
         if (needb > 0) { while (sv.ctl->lat_prog[w + 1] < needb) {} }
       }
       __threadfence_block();
       WV_DBG_ADD(1, t1 - t0); WV_DBG_ADD(2, t2 - t1); WV_DBG_ADD(3, WV_CLK() - t2);
     }
-    const double* Erow = sv.E + (size_t)(i & (L.R - 1)) * L.es;
-    double mulb = Erow[bcol];
-    double mull[H];
+    // emissions of the whole group up front (rows past T_i are stale ring memory: loaded, never used)
+    const double* Erow0 = sv.E + (size_t)(i0 & (L.R - 1)) * L.es;
+    double mb[G], ml[G][H];
 #pragma unroll
-    for (int h = 0; h < H; h++) mull[h] = Erow[ecol[h]];
-    const bool snap = (i & 1) == 0, apply = !snap;
-
-    // boundary cell from the previous lane / the previous warp
-    double bxs = __shfl_up_sync(FULL, x[K - 1], 1) * fb;
-    if (NW > 1 && w > 0) {
-      if (i > 0) {
+    for (int k = 0; k < G; k++) {
+      mb[k] = Erow0[(size_t)k * L.es + bcol];
+#pragma unroll
+      for (int h = 0; h < H; h++) ml[k][h] = Erow0[(size_t)k * L.es + ecol[h]];
+    }
+    uint32_t* const valw0 = sv.valw + ((size_t)(i0 & (L.RV - 1)) * LANES + g) * K;
+    int* const vale0 = sv.vale + (size_t)(i0 & (L.RV - 1)) * LANES + g;
+#pragma unroll
+    for (int k = 0; k < G; k++) {
+      const int i = i0 + k;
+      if (i < Ti) {
+        const bool apply = k == 0 && pending;
+        // boundary cell from the previous lane; from the previous warp the slot load is issued here and consumed below
+        double bxs = __shfl_up_sync(FULL, x[K - 1], 1) * fb;
         const uint4* slot = bnd_in + ((i - 1) & (RB - 1));
-        uint4 q;
-        const long long t0 = WV_CLK();
-        do { q = wv_ld_volatile_v4(slot); } while ((int)q.w != i);
-        WV_DBG_ADD(4, WV_CLK() - t0);
-        if (lane == 0) {
-          src_e = (int)q.z;
-          bxs = __hiloint2double((int)q.y, (int)q.x) * pow2i(src_e - e);
+        uint4 q = make_uint4(0u, 0u, 0u, 0u);
+        if (has_in && i > 0) q = wv_ld_volatile_v4(slot);
+        if (k == 2) {
+          // where the lane's scale should move (applied at the next group's first frame): block maximum into [1,2)
+          int mhi = 0;
+#pragma unroll
+          for (int j = 0; j < K; j++) mhi = max(mhi, __double2hiint(x[j]));
+          // a massless lane takes the new exponent of the nearest lane with mass below it (the side its mass will
+          // come from; below the first such lane of warps > 0: the exponent of the last boundary value), so that
+          // the mass front always runs into lanes whose scale is at most a few frames stale
+          const unsigned live = __ballot_sync(FULL, mhi != 0);
+          const unsigned below = live & ((1u << lane) - 1u);
+          const int own = e + ((mhi >> 20) - 1023);
+          const int from = __shfl_sync(FULL, own, below ? 31 - __clz(below) : 0);
+          const int en = mhi != 0 ? own : (below ? from : (has_in ? src_e : e));
+          const int nb_en = __shfl_up_sync(FULL, en, 1);
+          en_next = en;
+          f_next = pow2i(e - en);
+          fb_next = lane == 0 ? 0.0 : pow2i(nb_en - en);
+          pending = true;
         }
+        double mulb = mb[k], mull[H];
+#pragma unroll
+        for (int h = 0; h < H; h++) mull[h] = ml[k][h];
+        if (apply) {
+          mulb *= f_next;
+#pragma unroll
+          for (int h = 0; h < H; h++) mull[h] *= f_next;
+        }
+        // cell j gathers j, j-1 and (label cells, when allowed) j-2 of the previous frame; in place, top down
+        double so[K];
+#pragma unroll
+        for (int j = K - 1; j >= 2; j--) {
+          double a = x[j] + x[j - 1];
+          if (j & 1) a = fma(skipd[j >> 1], x[j - 2], a);
+          so[j] = a;
+          x[j] = a * ((j & 1) ? mull[j >> 1] : mulb);
+        }
+        if (has_in && i > 0) {
+          const long long t0 = WV_CLK();
+          while ((int)q.w != i) q = wv_ld_volatile_v4(slot);
+          WV_DBG_ADD(4, WV_CLK() - t0);
+          if ((int)q.z != src_e || e != fin_e) { src_e = (int)q.z; fin_e = e; fin = pow2i(src_e - e); }
+          if (lane == 0) bxs = __hiloint2double((int)q.y, (int)q.x) * fin;
+        }
+        {
+          so[1] = fma(skipd[0], bxs, x[1] + x[0]);
+          x[1] = so[1] * mull[0];
+          so[0] = x[0] + bxs;
+          x[0] = so[0] * mulb;
+        }
+        // drop the frame into the val ring: alpha with its emission (forward), beta before its emission (backward)
+        {
+          uint32_t wd[K];
+#pragma unroll
+          for (int j = 0; j < K; j++) wd[j] = (uint32_t)(BWD ? __double2hiint(so[j]) : __double2hiint(x[j]));
+#pragma unroll
+          for (int u = 0; u < K / 4; u++)
+            reinterpret_cast<uint4*>(valw0 + (size_t)k * LANES * K)[u] = make_uint4(wd[4 * u], wd[4 * u + 1], wd[4 * u + 2], wd[4 * u + 3]);
+          vale0[(size_t)k * LANES] = BWD ? e : (apply ? en_next : e);
+        }
+        if (apply) { e = en_next; fb = fb_next; }
+        if (has_out && lane == 31)
+          wv_st_volatile_v4(bnd_out + (i & (RB - 1)),
+                            make_uint4((uint32_t)__double2loint(x[K - 1]), (uint32_t)__double2hiint(x[K - 1]), (uint32_t)e, (uint32_t)(i + 1)));
       }
     }
-
-    if (snap) {
-      // where the lane's scale should move (applied next frame): block maximum into [1,2)
-      int mhi = 0;
-#pragma unroll
-      for (int j = 0; j < K; j++) mhi = max(mhi, __double2hiint(x[j]));
-      int nb_e = __shfl_up_sync(FULL, e, 1);
-      if (lane == 0) nb_e = (NW > 1 && w > 0) ? src_e : e;
-      const int en = mhi == 0 ? nb_e : e + ((mhi >> 20) - 1023);   // an all-zero lane follows the lane its mass will come from
-      const int nb_en = __shfl_up_sync(FULL, en, 1);
-      en_next = en;
-      f_next = pow2i(e - en);
-      fb_next = lane == 0 ? 0.0 : pow2i(nb_en - en);
-    }
-    if (apply) {
-      mulb *= f_next;
-#pragma unroll
-      for (int h = 0; h < H; h++) mull[h] *= f_next;
-    }
-    // cell j gathers j, j-1 and (label cells, when allowed) j-2 of the previous frame; in place, top down
-    double so[K];
-#pragma unroll
-    for (int j = K - 1; j >= 2; j--) {
-      double a = x[j] + x[j - 1];
-      if ((j & 1) && (skipm & (1u << (j >> 1)))) a += x[j - 2];
-      so[j] = a;
-      x[j] = a * ((j & 1) ? mull[j >> 1] : mulb);
-    }
-    {
-      double a = x[1] + x[0];
-      if (skipm & 1u) a += bxs;
-      so[1] = a;
-      x[1] = a * mull[0];
-      so[0] = x[0] + bxs;
-      x[0] = so[0] * mulb;
-    }
-    // drop the frame into the val ring: alpha with its emission (forward), beta before its emission (backward)
-    {
-      const size_t ent = (size_t)(i & (L.RV - 1)) * LANES + g;
-      uint32_t wd[K];
-#pragma unroll
-      for (int j = 0; j < K; j++) wd[j] = (uint32_t)(BWD ? __double2hiint(so[j]) : __double2hiint(x[j]));
-#pragma unroll
-      for (int u = 0; u < K / 4; u++)
-        reinterpret_cast<uint4*>(sv.valw + ent * K)[u] = make_uint4(wd[4 * u], wd[4 * u + 1], wd[4 * u + 2], wd[4 * u + 3]);
-      sv.vale[ent] = BWD ? e : (apply ? en_next : e);
-    }
-    if (apply) { e = en_next; fb = fb_next; }
-    if (NW > 1 && w + 1 < NW && lane == 31)
-      wv_st_volatile_v4(bnd_out + (i & (RB - 1)),
-                        make_uint4((uint32_t)__double2loint(x[K - 1]), (uint32_t)__double2hiint(x[K - 1]), (uint32_t)e, (uint32_t)(i + 1)));
-    if ((i & (CF - 1)) == CF - 1 || i == Ti - 1) {
+    if (((i0 + G) & (CF - 1)) == 0 || i0 + G >= Ti) {
       __syncwarp();
-      if (lane == 0) { __threadfence_block(); sv.ctl->lat_prog[w] = i + 1; }
+      if (lane == 0) { __threadfence_block(); sv.ctl->lat_prog[w] = min(i0 + G, Ti); }
     }
   }
   WV_DBG_ADD(0, WV_CLK() - tstart);
@@ -385,36 +412,12 @@ __device__ void wave_lattice(const WaveParams& p, const WaveView& sv, int b, int
 }
 
 // ---- combiner warps ---------------------------------------------------------------------------------
-// The K cells of lattice lane g in one frame, multiplied with the same cells of the other sweep's stored row:
-// pr[j] = (my cell) * (other cell) as a double of the two 32-bit tops, El[j] = sum of the two block exponents.
-template <int K>
-__device__ __forceinline__ void wave_pair_cells(const uint32_t* valw_row, const int* vale_row, const uint32_t* orow, int cells,
-                                                int S, int g, double (&pr)[K], int (&El)[K]) {
-  constexpr int KLOG = K == 4 ? 2 : 3;
-  uint32_t wd[K];
-#pragma unroll
-  for (int v = 0; v < K / 4; v++) {
-    const uint4 t4 = reinterpret_cast<const uint4*>(valw_row + (size_t)g * K)[v];
-    wd[4 * v] = t4.x; wd[4 * v + 1] = t4.y; wd[4 * v + 2] = t4.z; wd[4 * v + 3] = t4.w;
-  }
-  const int em = vale_row[g];
-#pragma unroll
-  for (int j = 0; j < K; j++) {
-    const int mp = S - 1 - (g * K + j);          // the same lattice cell in the other sweep's indexing
-    const bool valid = mp >= 0;
-    const int mpc = valid ? mp : 0;
-    const uint32_t ow = orow[mpc];
-    const int oe = (int)orow[cells + (mpc >> KLOG)];
-    pr[j] = valid ? wv_hi2d(wd[j]) * wv_hi2d(ow) : 0.0;
-    El[j] = em + oe;
-  }
-}
-
 template <int K, int NW>
 __device__ void wave_combiner(const WaveParams& p, const WaveView& sv, int b, int Ti, int Li, int q, int lane, bool BWD, long long* dbgp) {
   const long long tstart = WV_CLK();
   constexpr unsigned FULL = 0xffffffffu;
-  constexpr int LANES = 32 * NW, CELLS = LANES * K, ROWW = LANES * (K + 1), PF = kWavePF;
+  constexpr int H = K / 2, LANES = 32 * NW, CELLS = LANES * K, ROWW = LANES * (K + 1), PF = kWavePF;
+  constexpr int KLOG = K == 4 ? 2 : 3;
   const WaveLayout& L = p.L;
   const int NC = L.NC;
   const int S = 2 * Li + 1;
@@ -477,8 +480,20 @@ __device__ void wave_combiner(const WaveParams& p, const WaveView& sv, int b, in
   const long long tsecond = WV_CLK();
   for (int u = 0; u < PF; u++) { prefetch(i + u * NC, u); wv_cp_async_commit(); }
 
+  // Per lane: the lattice lanes g = lane + 32u it multiplies.  My cell m = g*K + j is the other sweep's cell
+  // mp = S-1-m (cells past S carry zero mass on my side, so a clamped index is enough there).
+  int mp0[NW];              // other-sweep index of my cell j = 0
+  uint32_t* lcol[NW][H];    // accumulator of the label of cell j = 2h+1 (blank past L_i: receives zeros)
+#pragma unroll
+  for (int u = 0; u < NW; u++) {
+    const int g = lane + 32 * u;
+    mp0[u] = S - 1 - g * K;
+#pragma unroll
+    for (int h = 0; h < H; h++) lcol[u][h] = acc + sv.lab[g * H + h];
+  }
+
   bool have_z = false;
-  double cz = 0.0;   // 2^31 / Z
+  double cz = 0.0;   // 2^31 / Z as mantissa in [1,2); its exponent is folded into Ez
   int Ez = 0;
   const float sc = (float)p.scale;
   for (int k = 0; i < Ti; i += NC, ++k) {
@@ -488,49 +503,58 @@ __device__ void wave_combiner(const WaveParams& p, const WaveView& sv, int b, in
     const size_t ent0 = (size_t)(i & (L.RV - 1)) * LANES;
     const uint32_t* valw_row = sv.valw + ent0 * K;
     const int* vale_row = sv.vale + ent0;
+    double pr[NW][K];
+    int El[NW][K];
+#pragma unroll
+    for (int u = 0; u < NW; u++) {
+      const int g = lane + 32 * u;
+      uint32_t wd[K];
+#pragma unroll
+      for (int v = 0; v < K / 4; v++) {
+        const uint4 t4 = reinterpret_cast<const uint4*>(valw_row + (size_t)g * K)[v];
+        wd[4 * v] = t4.x; wd[4 * v + 1] = t4.y; wd[4 * v + 2] = t4.z; wd[4 * v + 3] = t4.w;
+      }
+      const int em = vale_row[g];
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        const int mpc = max(mp0[u] - j, 0);
+        // my cell S (the first one past the lattice) is nonzero BEFORE its emission in the backward sweep
+        pr[u][j] = mp0[u] >= j ? wv_hi2d(wd[j]) * wv_hi2d(orow[mpc]) : 0.0;
+        El[u][j] = em + (int)orow[CELLS + (mpc >> KLOG)];
+      }
+    }
     if (!have_z) {
       // Z = sum_s alpha(t,s) * beta(t,s), the same for every frame: taken once per combiner warp
       int emax = 4 * kNegExp;
-#pragma unroll 1
-      for (int u = 0; u < NW; u++) {
-        double pr[K]; int El[K];
-        wave_pair_cells<K>(valw_row, vale_row, orow, CELLS, S, lane + 32 * u, pr, El);
 #pragma unroll
-        for (int j = 0; j < K; j++) if (pr[j] > 0.0) emax = max(emax, El[j]);
-      }
+      for (int u = 0; u < NW; u++)
+#pragma unroll
+        for (int j = 0; j < K; j++) if (pr[u][j] > 0.0) emax = max(emax, El[u][j]);
       emax = warp_max_int(emax);
       double tot = 0.0;
-#pragma unroll 1
-      for (int u = 0; u < NW; u++) {
-        double pr[K]; int El[K];
-        wave_pair_cells<K>(valw_row, vale_row, orow, CELLS, S, lane + 32 * u, pr, El);
 #pragma unroll
-        for (int j = 0; j < K; j++) if (pr[j] > 0.0) tot += pr[j] * pow2i(El[j] - emax);
-      }
+      for (int u = 0; u < NW; u++)
+#pragma unroll
+        for (int j = 0; j < K; j++) if (pr[u][j] > 0.0) tot += pr[u][j] * pow2i(El[u][j] - emax);
       tot = warp_sum(tot);
-      cz = 2147483648.0 / tot;   // tot == 0: the lattice tail flags the utterance and the block is overwritten with NaN
-      Ez = emax;
+      // 2^31 / Z = cz * 2^kz with cz in [1,2): the power of two moves into Ez, so the per-cell scale
+      // 2^(El - Ez) * cz stays finite whatever stale exponent a massless lane carries (0 * finite = 0).
+      // tot == 0 or NaN: the lattice tail flags the utterance and the block is overwritten with NaN.
+      const double r = 2147483648.0 / tot;
+      const int kz = ((__double2hiint(r) >> 20) & 0x7ff) - 1023;
+      cz = __hiloint2double((__double2hiint(r) & 0x800fffff) | 0x3ff00000, __double2loint(r));
+      Ez = emax - kz;
       have_z = true;
     }
     // posteriors summed per symbol: fixed point 2^-31 (the sum per symbol is <= 1), integer adds commute
     uint32_t bsum = 0u;
-#pragma unroll 1
+#pragma unroll
     for (int u = 0; u < NW; u++) {
-      const int g = lane + 32 * u;
-      double pr[K]; int El[K];
-      wave_pair_cells<K>(valw_row, vale_row, orow, CELLS, S, g, pr, El);
 #pragma unroll
       for (int j = 0; j < K; j++) {
-        // lanes the mass has not reached carry stale block exponents: their scale may overflow (0 * inf);
-        // anything that is not a posterior (<= 1, i.e. <= 2^31 here) counts as zero
-        const double pv = pr[j] * (pow2i(El[j] - Ez) * cz);
-        const uint32_t qv = pv < 2149580800.0 ? __double2uint_rn(pv) : 0u;
-        if (j & 1) {
-          const int li = (g * K + j) >> 1;
-          if (li < Li) atomicAdd(acc + sv.lab[li], qv);
-        } else {
-          bsum += qv;
-        }
+        const uint32_t qv = __double2uint_rn(pr[u][j] * (pow2i(El[u][j] - Ez) * cz));
+        if (j & 1) atomicAdd(lcol[u][j >> 1], qv);
+        else bsum += qv;
       }
     }
     const uint32_t qb = __reduce_add_sync(FULL, bsum);
@@ -565,12 +589,29 @@ template <int K, int NW>
 __device__ void wave_roles(const WaveParams& p, const WaveView& sv, int b, int Ti, int Li, int w, int lane, bool BWD) {
   const WaveLayout& L = p.L;
   long long* dbgp = (p.dbg != nullptr && b == 0 && lane == 0 && w < 16) ? p.dbg + ((BWD ? 16 : 0) + w) * 8 : nullptr;
-  const int first_comb = L.NP, first_lat = L.NP + L.NC;
-  if (w >= first_lat) {
-    wave_lattice<K, NW>(p, sv, b, Ti, Li, w - first_lat, lane, BWD, dbgp);
-  } else if (w >= first_comb) {
-    wave_combiner<K, NW>(p, sv, b, Ti, Li, w - first_comb, lane, BWD, dbgp);
+  // Warp w runs on scheduler (SM sub-partition) w % 4, each with its own small L0 instruction cache.  With
+  // `by_smsp` the roles are laid out so that every sub-partition runs ONE role's loop (lattice on 0,
+  // combiners on 1 and 2, producers on 3): three interleaved loops do not fit an L0 and the sweep
+  // starves on instruction fetch otherwise.
+  int role, idx;   // 0 lattice, 1 combiner, 2 producer, 3 idle
+  if (L.by_smsp) {
+    const int sub = w & 3, r = w >> 2;
+    if (sub == 0) { role = r < NW ? 0 : 3; idx = r; }
+    else if (sub == 3) { role = r < L.NP ? 2 : 3; idx = r; }
+    else { idx = 2 * r + (sub - 1); role = idx < L.NC ? 1 : 3; }
   } else {
+    const int first_comb = L.NP, first_lat = L.NP + L.NC;
+    if (w >= first_lat) { role = 0; idx = w - first_lat; }
+    else if (w >= first_comb) { role = 1; idx = w - first_comb; }
+    else { role = 2; idx = w; }
+  }
+  if (role == 0) {
+    if (BWD) wave_lattice<K, NW, true>(p, sv, b, Ti, Li, idx, lane, dbgp);
+    else wave_lattice<K, NW, false>(p, sv, b, Ti, Li, idx, lane, dbgp);
+  } else if (role == 1) {
+    wave_combiner<K, NW>(p, sv, b, Ti, Li, idx, lane, BWD, dbgp);
+  } else if (role == 2) {
+    w = idx;
     wave_producer<NW>(p, sv, b, Ti, w, lane, BWD, dbgp);
     // padding frames t >= T_i: exp(lp) for log-prob input (the engine contract, ctc_loss.cpp:105-117),
     // 0 for fused-logits input (what the reference's log_softmax backward leaves there)
@@ -587,7 +628,7 @@ __device__ void wave_roles(const WaveParams& p, const WaveView& sv, int b, int T
 }
 
 template <int K, int NW>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (NW + 8), 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (NW <= 4 ? 16 : 32), 1)
 ctc_wave_kernel(const WaveParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int H = K / 2, LANES = 32 * NW;
@@ -693,7 +734,7 @@ int launch_wave_k(const WaveParams& wp, cudaStream_t s) {
     E2E_CUDA_TRY(cudaFuncSetAttribute(ctc_wave_kernel<K, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, wp.L.total));
     attr_smem = wp.L.total;
   }
-  const unsigned threads = 32u * (unsigned)(NW + wp.L.NC + wp.L.NP);
+  const unsigned threads = 32u * (unsigned)wp.L.nwarps;
   KernelTimer timer(kKernelLattice, s);
   ctc_wave_kernel<K, NW><<<2u * (unsigned)wp.B, threads, (size_t)wp.L.total, s>>>(wp);
   E2E_CUDA_TRY(cudaGetLastError());
