@@ -212,7 +212,9 @@ def run_ours(args, wl):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(3, args.warmup)):
+    # warm-up: at least W steps, and at least one pass over the rotating batches so that every batch's gradient
+    # buffer exists before the timed region (a first-touch cudaMalloc inside it would time the allocator)
+    for i in range(max(3, args.warmup, n_rot)):
         step(i)
     barrier()
     try:

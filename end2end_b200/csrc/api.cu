@@ -165,7 +165,11 @@ static bool make_sweep_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
 // Wave kernel (fused small-alphabet path): variants by (cells per lane, lattice warps per sweep).
 static bool make_wave_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   if (!fused || d.dtype == E2E_F64 || d.alphabet > kDenseMaxAlphabet) return false;
-  if (env_int("E2E_CTC_WAVE", 0) == 0 || env_int("E2E_CTC_NO_FUSED", 0) || env_int("E2E_CTC_LEGACY", 0) ||
+  // E2E_CTC_WAVE: 0 never, 1 whenever a variant fits (testing), unset: latency shapes only -- every
+  // utterance's two CTAs resident at once (2B <= 148 SMs) and at most four lattice warps per sweep; larger
+  // batches are throughput-bound and run the one-warp-per-sweep kernel.
+  const int mode = env_int("E2E_CTC_WAVE", -1);
+  if (mode == 0 || env_int("E2E_CTC_NO_FUSED", 0) || env_int("E2E_CTC_LEGACY", 0) ||
       env_int("E2E_CTC_CELLS_PER_LANE", 0) || env_int("E2E_CTC_LATTICE_WARPS", 0)) return false;
   static const int kVar[][2] = {{4, 1}, {4, 2}, {4, 4}, {4, 8}, {8, 8}};
   const int S = 2 * d.max_targets + 1;
@@ -173,13 +177,15 @@ static bool make_wave_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   int K = 0, NW = 0;
   for (const auto& v : kVar)
     if (32 * v[0] * v[1] >= S && (!fw || v[1] == fw) && (!fk || v[0] == fk) && !K) { K = v[0]; NW = v[1]; }
+  if (mode != 1 && (2 * d.batch > 148 || NW > 4)) return false;
   if (!K) return false;
   WaveLayout L;
   L.K = K; L.NW = NW;
-  L.NC = env_int("E2E_CTC_WAVE_NC", NW >= 4 ? 8 : 2);
-  L.NP = env_int("E2E_CTC_WAVE_NP", NW >= 4 ? 4 : 1);
+  L.NC = env_int("E2E_CTC_WAVE_NC", NW >= 4 ? 4 : 2);
+  L.NP = env_int("E2E_CTC_WAVE_NP", NW >= 4 ? 2 : 1);
   if (L.NC < 1 || L.NC > 8 || (L.NP != 1 && L.NP != 2 && L.NP != 4)) return false;
-  L.by_smsp = env_int("E2E_CTC_WAVE_BY_SMSP", NW >= 4 ? 1 : 0);
+  L.nap = env_int("E2E_CTC_WAVE_NAP", 32);
+  L.by_smsp = env_int("E2E_CTC_WAVE_BY_SMSP", 0);
   if (L.by_smsp) {
     int r = NW > L.NP ? NW : L.NP;
     if ((L.NC + 1) / 2 > r) r = (L.NC + 1) / 2;
@@ -189,11 +195,12 @@ static bool make_wave_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   }
   if (L.nwarps > (NW <= 4 ? 16 : 32)) return false;
   const int lanes = 32 * NW, roww = lanes * (K + 1);
-  L.es = d.alphabet + 2;
+  L.es = (d.alphabet + 2) | 1;   // odd: the producer's lane-per-frame stores are bank-conflict free
   L.vpad = (d.alphabet + 3) & ~3;
   L.RV = env_int("E2E_CTC_WAVE_RV", lanes * K >= 1024 ? 16 : 32);
-  L.R = 64;
-  while (L.R > 16 && (size_t)L.R * L.es * 8 > 48 * 1024) L.R >>= 1;
+  L.R = env_int("E2E_CTC_WAVE_R", 128);   // producer blocks are 32 frames: two per producer in flight
+  if (L.R < 64 || (L.R & (L.R - 1))) return false;
+  while (L.R > 64 && (size_t)L.R * L.es * 8 > (size_t)(NW >= 4 ? 64 : 40) * 1024) L.R >>= 1;
   if (L.RV > L.R / 2) L.RV = L.R / 2;
   if (L.RV < kWaveCF || (L.RV & (L.RV - 1))) return false;
   size_t off = 0;
@@ -201,8 +208,8 @@ static bool make_wave_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   L.off_E = (int)off; off = (size_t)align16i(off + (size_t)L.R * L.es * 8);
   L.off_valw = (int)off; off += (size_t)L.RV * lanes * K * 4;
   L.off_vale = (int)off; off += (size_t)L.RV * lanes * 4;
-  L.off_stage = (int)off; off += (size_t)L.NC * kWavePF * roww * 4;
-  L.off_acc = (int)off; off += (size_t)L.NC * L.vpad * 4;
+  L.off_stage = (int)off; off += (size_t)L.NC * kWavePF * (roww + 4) * 4;
+  L.off_acc = (int)off; off += (size_t)L.NC * 4 * L.vpad * 4;
   L.off_bnd = (int)off; off += (size_t)NW * kWaveRB * 16;
   L.off_ctl = (int)off; off += wave_ctl_bytes();
   L.total = (int)off;

@@ -43,6 +43,7 @@ struct WaveLayout {
   int NP, NC;       // producer (row log-softmax) warps, combiner warps
   int by_smsp;      // lay the roles out by SM sub-partition (warp id % 4): latency configurations
   int nwarps;       // warps per CTA
+  int nap;          // nanoseconds a waiting producer / combiner warp sleeps between polls (0: spin)
   int R, RV;        // frames in the emission ring / in the val ring (powers of two)
   int es;           // doubles per emission-ring frame: V symbols, a zero column, the row normaliser
   int vpad;         // u32 posterior accumulators per combiner warp

@@ -30,6 +30,7 @@
 //    snapshot of the previous frame, folded into the emission multipliers (ctc_sweep_impl.cuh scheme).
 #pragma once
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -51,7 +52,7 @@ struct WaveParams {
 
 // control block (shared memory, ints)
 struct WaveCtl {
-  volatile int e_ready[4];       // producer pw: chunks pw, pw+NP, ... up to (value-1) are in the E ring
+  volatile int e_ready[4];       // producer pw: its 32-frame blocks pw, pw+NP, ... below this value are in the E ring
   volatile int lat_prog[8];      // lattice warp w: frames [0, value) swept and dropped into the val ring
   volatile int comb_done[8];     // combiner q: the next frame it will take (all its earlier frames are done)
   int zero;                      // no path survives / NaN input
@@ -74,6 +75,11 @@ __device__ __forceinline__ uint4 wv_ld_volatile_v4(const void* p) {
   asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(wv_smem_u32(p)));
   return r;
 }
+// the same store, predicated inside the asm so that the caller stays branch-free
+__device__ __forceinline__ void wv_st_volatile_v4_if(void* p, uint4 v, int on) {
+  asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.s32 pp, %5, 0;\n\t@pp st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};\n\t}"
+               ::"r"(wv_smem_u32(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(on));
+}
 __device__ __forceinline__ void wv_st_volatile_v4(void* p, uint4 v) {
   asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(wv_smem_u32(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
@@ -87,12 +93,15 @@ __device__ __forceinline__ double wv_hi2d(uint32_t h) { return __hiloint2double(
 // p(t, v) relative to the row's log-sum-exp, as a double: the exponent argument is formed as torch's fp32
 // log_softmax does ((x - max) - logsum, fp32) for raw logits, so the emission equals exp(double(lp32)) of the
 // reference up to one fp32 exp rounding.
-__device__ __noinline__ double wv_emission(float x, float m, float ls, int from_logits) {
-  if (from_logits) return (double)expf((x - m) - ls);
+__device__ __noinline__ double wv_emission_lp(float x, float m, float ls) {
   const double d = (double)x - ((double)m + (double)ls);
   const float hi = (float)d;
   const float lo = (float)(d - (double)hi);
   return (double)expf(hi) * (1.0 + (double)lo);
+}
+__device__ __forceinline__ double wv_emission(float x, float m, float ls, int from_logits) {
+  if (from_logits) return (double)expf((x - m) - ls);
+  return wv_emission_lp(x, m, ls);
 }
 
 struct WaveView {
@@ -128,124 +137,80 @@ __device__ __forceinline__ int wv_min_prog(const volatile int* a, int n) {
 }
 
 // ---- producers: fused row log-softmax -> E ring ---------------------------------------------------
-// NF frames at a time: all row loads are issued before the first use and the warp reductions of the NF
-// frames are interleaved (offset-major), so a batch costs a few shuffle latencies, not NF times that.
-template <int NQ>
-__device__ __noinline__ double wave_produce_frames(const WaveParams& p, const WaveView& sv, long long xbase, int Ti,
-                                                   int i0, int lane, bool BWD) {
-  constexpr unsigned FULL = 0xffffffffu;
-  constexpr int NF = 4;
+// A producer warp converts a block of 32 frames at a time with ONE LANE PER FRAME: no cross-lane reductions, so
+// a row costs ~25 instructions per frame instead of ~110 with warp-shuffle max / sum.  The lanes read 32
+// different rows per load instruction; the rows are consecutive in memory (or at least each row is one or two
+// 128-byte lines), so after the first touch the loads are L1 hits.  REG (V <= 32): the row stays in registers.
+constexpr int kWavePB = 32;   // frames per producer block
+
+__device__ __forceinline__ float wv_load_logit(const void* base, int dtype, long long idx) {
+  if (dtype == E2E_F32) return __ldg(reinterpret_cast<const float*>(base) + idx);
+  const unsigned short r = __ldg(reinterpret_cast<const unsigned short*>(base) + idx);
+  return dtype == E2E_BF16 ? __uint_as_float((uint32_t)r << 16) : __half2float(__ushort_as_half(r));
+}
+
+template <bool REG>
+__device__ __noinline__ double wave_produce_block(const WaveParams& p, const WaveView& sv, long long xbase, int Ti,
+                                                  int i0, int lane, bool BWD) {
   const WaveLayout& L = p.L;
-  const int nf = min(NF, Ti - i0);
-  float xv[NF][NQ];
-  if (p.dtype == E2E_F32) {
-    const float* base = reinterpret_cast<const float*>(p.logits);
+  const int i = i0 + lane;
+  if (i >= Ti) return 0.0;
+  const long long ro = xbase + (long long)(BWD ? (Ti - 1 - i) : i) * p.st;
+  double* Erow = sv.E + (size_t)(i & (L.R - 1)) * L.es;
+  const int V = p.V;
+  float m = -INFINITY, s = 0.f;
+  bool nan = false;
+  if (REG) {
+    float xv[32];
 #pragma unroll
-    for (int f = 0; f < NF; f++) {
-      const int i = min(i0 + f, Ti - 1);
-      const long long ro = xbase + (long long)(BWD ? (Ti - 1 - i) : i) * p.st;
+    for (int v = 0; v < 32; v++) xv[v] = v < V ? wv_load_logit(p.logits, p.dtype, ro + v) : -INFINITY;
 #pragma unroll
-      for (int q = 0; q < NQ; q++) {
-        const int v = lane + 32 * q;
-        xv[f][q] = (f < nf && v < p.V) ? __ldg(base + ro + v) : -INFINITY;
-      }
-    }
+    for (int v = 0; v < 32; v++) { nan |= xv[v] != xv[v]; m = fmaxf(m, xv[v]); }
+#pragma unroll
+    for (int v = 0; v < 32; v++) s += expf(xv[v] - m);   // exp(-inf) = 0 for the padding columns
+    float ls = logf(s);
+    if (nan) { m = NAN; ls = NAN; }
+#pragma unroll
+    for (int v = 0; v < 32; v++) if (v < V) Erow[v] = wv_emission(xv[v], m, ls, p.from_logits);
+    const double mls = (double)m + (double)ls;
+    Erow[V] = 0.0;                                       // the column padding cells read
+    Erow[V + 1] = p.from_logits ? 1.0 : exp(mls);        // turns the emission back into exp(x)
+    return mls;
   } else {
-    const unsigned short* base = reinterpret_cast<const unsigned short*>(p.logits);
-    unsigned short rw[NF][NQ];
-#pragma unroll
-    for (int f = 0; f < NF; f++) {
-      const int i = min(i0 + f, Ti - 1);
-      const long long ro = xbase + (long long)(BWD ? (Ti - 1 - i) : i) * p.st;
-#pragma unroll
-      for (int q = 0; q < NQ; q++) {
-        const int v = lane + 32 * q;
-        rw[f][q] = (f < nf && v < p.V) ? __ldg(base + ro + v) : (unsigned short)0;
-      }
-    }
-#pragma unroll
-    for (int f = 0; f < NF; f++)
-#pragma unroll
-      for (int q = 0; q < NQ; q++) {
-        const int v = lane + 32 * q;
-        const float x = p.dtype == E2E_BF16 ? __uint_as_float((uint32_t)rw[f][q] << 16) : __half2float(__ushort_as_half(rw[f][q]));
-        xv[f][q] = (f < nf && v < p.V) ? x : -INFINITY;
-      }
+    for (int v = 0; v < V; v++) { const float x = wv_load_logit(p.logits, p.dtype, ro + v); nan |= x != x; m = fmaxf(m, x); }
+    for (int v = 0; v < V; v++) s += expf(wv_load_logit(p.logits, p.dtype, ro + v) - m);
+    float ls = logf(s);
+    if (nan) { m = NAN; ls = NAN; }
+    for (int v = 0; v < V; v++) Erow[v] = wv_emission(wv_load_logit(p.logits, p.dtype, ro + v), m, ls, p.from_logits);
+    const double mls = (double)m + (double)ls;
+    Erow[V] = 0.0;
+    Erow[V + 1] = p.from_logits ? 1.0 : exp(mls);
+    return mls;
   }
-  float m[NF], s[NF];
-  bool nan[NF];
-#pragma unroll
-  for (int f = 0; f < NF; f++) {
-    float mm = xv[f][0];
-    bool nn = xv[f][0] != xv[f][0];
-#pragma unroll
-    for (int q = 1; q < NQ; q++) { mm = fmaxf(mm, xv[f][q]); nn |= xv[f][q] != xv[f][q]; }
-    m[f] = mm; nan[f] = nn;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-    for (int f = 0; f < NF; f++) m[f] = fmaxf(m[f], __shfl_xor_sync(FULL, m[f], o));
-#pragma unroll
-  for (int f = 0; f < NF; f++) {
-    nan[f] = __any_sync(FULL, nan[f]);
-    float ss = 0.f;
-#pragma unroll
-    for (int q = 0; q < NQ; q++) ss += expf(xv[f][q] - m[f]);   // exp(-inf) = 0 for the padding lanes
-    s[f] = ss;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-    for (int f = 0; f < NF; f++) s[f] += __shfl_xor_sync(FULL, s[f], o);
-  double lse = 0.0;
-#pragma unroll
-  for (int f = 0; f < NF; f++) {
-    if (f < nf) {
-      float mf = m[f], ls = logf(s[f]);
-      if (nan[f]) { mf = NAN; ls = NAN; }
-      double* Erow = sv.E + (size_t)((i0 + f) & (L.R - 1)) * L.es;
-#pragma unroll
-      for (int q = 0; q < NQ; q++) {
-        const int v = lane + 32 * q;
-        if (v < p.V) Erow[v] = wv_emission(xv[f][q], mf, ls, p.from_logits);
-      }
-      if (lane == 0) {
-        const double mls = (double)mf + (double)ls;
-        Erow[p.V] = 0.0;                                       // the column padding cells read
-        Erow[p.V + 1] = p.from_logits ? 1.0 : exp(mls);        // turns the emission back into exp(x)
-        lse += mls;
-      }
-    }
-  }
-  return lse;
 }
 
 template <int NW>
 __device__ void wave_producer(const WaveParams& p, const WaveView& sv, int b, int Ti, int pw, int lane, bool BWD, long long* dbgp) {
   const long long tstart = WV_CLK();
-  constexpr int CF = kWaveCF;
+  constexpr int PB = kWavePB;
   const WaveLayout& L = p.L;
-  const int nchunks = (Ti + CF - 1) / CF;
+  const int nblocks = (Ti + PB - 1) / PB;
   const long long xbase = (long long)b * p.sb;
-  const int nq = (p.V + 31) >> 5;
   double lse = 0.0;
-  for (int c = pw; c < nchunks; c += L.NP) {
-    const int need = c * CF + CF - L.R;   // frames below `need` must have left the ring
+  for (int bi = pw; bi < nblocks; bi += L.NP) {
+    const int need = bi * PB + PB - L.R;   // frames below `need` must have left the ring
     if (need > 0) {
       const long long t0 = WV_CLK();
-      while (wv_min_prog<8>(sv.ctl->lat_prog, NW) < need || wv_min_prog<8>(sv.ctl->comb_done, L.NC) < need) __nanosleep(64);
+      while (wv_min_prog<8>(sv.ctl->lat_prog, NW) < need || wv_min_prog<8>(sv.ctl->comb_done, L.NC) < need) { if (L.nap) __nanosleep(L.nap); }
       __threadfence_block();
       WV_DBG_ADD(1, WV_CLK() - t0);
     }
-#pragma unroll 1
-    for (int i0 = c * CF; i0 < min(c * CF + CF, Ti); i0 += 4) {
-      if (nq == 1) lse += wave_produce_frames<1>(p, sv, xbase, Ti, i0, lane, BWD);
-      else lse += wave_produce_frames<4>(p, sv, xbase, Ti, i0, lane, BWD);
-    }
+    if (p.V <= 32) lse += wave_produce_block<true>(p, sv, xbase, Ti, bi * PB, lane, BWD);
+    else lse += wave_produce_block<false>(p, sv, xbase, Ti, bi * PB, lane, BWD);
     __syncwarp();
-    if (lane == 0) { __threadfence_block(); sv.ctl->e_ready[pw] = c + 1; }
+    if (lane == 0) { __threadfence_block(); sv.ctl->e_ready[pw] = bi + 1; }
   }
+  lse = warp_sum(lse);   // fixed order: deterministic loss for log-prob input
   if (lane == 0) sv.ctl->lse[pw] = lse;
   WV_DBG_ADD(0, WV_CLK() - tstart);
 }
@@ -287,29 +252,35 @@ __device__ void wave_lattice(const WaveParams& p, const WaveView& sv, int b, int
   int en_next = 0;
   double f_next = 1.0, fb_next = fb;
   bool pending = false;
-  int src_e = 0, fin_e = 0;            // boundary from the previous warp: its exponent, and my exponent `fin` was built for
-  double fin = 1.0;                    // 2^(src_e - fin_e)
+  int src_e = 0;                       // exponent of the last boundary value received from the previous warp
   const bool has_in = NW > 1 && w > 0, has_out = NW > 1 && w + 1 < NW;
   const uint4* const bnd_in = sv.bnd + (size_t)(w > 0 ? w - 1 : 0) * RB;
   uint4* const bnd_out = sv.bnd + (size_t)w * RB;
 
-  for (int i0 = 0; i0 < Ti; i0 += G) {
-    if ((i0 & (CF - 1)) == 0) {
-      const int c = i0 / CF;
-      const long long t0 = WV_CLK();
-      const volatile int* er = &sv.ctl->e_ready[c & (L.NP - 1)];
-      while (*er <= c) {}
-      const long long t1 = WV_CLK();
-      const int needv = i0 + CF - L.RV;
-      if (needv > 0) { while (wv_min_prog<8>(sv.ctl->comb_done, L.NC) < needv) {} }
-      const long long t2 = WV_CLK();
-      if (has_out) {
-        const int needb = i0 + CF - RB + 1;   // the slots this chunk overwrites have been read
-        if (needb > 0) { while (sv.ctl->lat_prog[w + 1] < needb) {} }
-      }
-      __threadfence_block();
-      WV_DBG_ADD(1, t1 - t0); WV_DBG_ADD(2, t2 - t1); WV_DBG_ADD(3, WV_CLK() - t2);
+  auto chunk_wait = [&](int i0) {
+    const int c = i0 / CF;
+    const long long t0 = WV_CLK();
+    const int bi = i0 / kWavePB;   // the producer block the chunk belongs to
+    const volatile int* er = &sv.ctl->e_ready[bi & (L.NP - 1)];
+    while (*er <= bi) {}
+    const long long t1 = WV_CLK();
+    const int needv = i0 + CF - L.RV;
+    if (needv > 0) { while (wv_min_prog<8>(sv.ctl->comb_done, L.NC) < needv) {} }
+    const long long t2 = WV_CLK();
+    if (has_out) {
+      const int needb = i0 + CF - RB + 1;   // the slots this chunk overwrites have been read
+      if (needb > 0) { while (sv.ctl->lat_prog[w + 1] < needb) {} }
     }
+    __threadfence_block();
+    WV_DBG_ADD(1, t1 - t0); WV_DBG_ADD(2, t2 - t1); WV_DBG_ADD(3, WV_CLK() - t2);
+  };
+
+  // One group of G frames.  FULLG (all G frames exist): the boundary slots of the whole group are fetched up
+  // front -- the warp waits for the previous warp to finish the group's third frame, so it runs one group
+  // behind it -- and the body is straight-line code the compiler can schedule across frames.  Otherwise (the
+  // last, partial group) every frame polls its own slot.
+  auto group = [&](auto full_c, int i0) {
+    constexpr bool FULLG = decltype(full_c)::value;
     // emissions of the whole group up front (rows past T_i are stale ring memory: loaded, never used)
     const double* Erow0 = sv.E + (size_t)(i0 & (L.R - 1)) * L.es;
     double mb[G], ml[G][H];
@@ -319,18 +290,34 @@ __device__ void wave_lattice(const WaveParams& p, const WaveView& sv, int b, int
 #pragma unroll
       for (int h = 0; h < H; h++) ml[k][h] = Erow0[(size_t)k * L.es + ecol[h]];
     }
+    uint4 qg[G];
+#pragma unroll
+    for (int k = 0; k < G; k++) qg[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (FULLG && has_in) {
+      const int last = i0 + G - 2;   // frame i needs the boundary of frame i-1
+      const long long t0 = WV_CLK();
+      do { qg[G - 1] = wv_ld_volatile_v4(bnd_in + (last & (RB - 1))); } while ((int)qg[G - 1].w != last + 1);
+      WV_DBG_ADD(4, WV_CLK() - t0);
+#pragma unroll
+      for (int k = 0; k < G - 1; k++) qg[k] = wv_ld_volatile_v4(bnd_in + ((i0 + k - 1) & (RB - 1)));
+    }
     uint32_t* const valw0 = sv.valw + ((size_t)(i0 & (L.RV - 1)) * LANES + g) * K;
     int* const vale0 = sv.vale + (size_t)(i0 & (L.RV - 1)) * LANES + g;
 #pragma unroll
     for (int k = 0; k < G; k++) {
       const int i = i0 + k;
-      if (i < Ti) {
+      if (FULLG || i < Ti) {
         const bool apply = k == 0 && pending;
-        // boundary cell from the previous lane; from the previous warp the slot load is issued here and consumed below
+        // boundary cell from the previous lane; from the previous warp through its slot
         double bxs = __shfl_up_sync(FULL, x[K - 1], 1) * fb;
         const uint4* slot = bnd_in + ((i - 1) & (RB - 1));
-        uint4 q = make_uint4(0u, 0u, 0u, 0u);
-        if (has_in && i > 0) q = wv_ld_volatile_v4(slot);
+        uint4 q = qg[k];
+        if (!FULLG && has_in && i > 0) q = wv_ld_volatile_v4(slot);
+        if (FULLG && has_in && i > 0) {
+          src_e = (int)q.z;
+          const double bin = __hiloint2double((int)q.y, (int)q.x) * pow2i(src_e - e);
+          if (lane == 0) bxs = bin;
+        }
         if (k == 2) {
           // where the lane's scale should move (applied at the next group's first frame): block maximum into [1,2)
           int mhi = 0;
@@ -367,12 +354,13 @@ __device__ void wave_lattice(const WaveParams& p, const WaveView& sv, int b, int
           so[j] = a;
           x[j] = a * ((j & 1) ? mull[j >> 1] : mulb);
         }
-        if (has_in && i > 0) {
+        if (!FULLG && has_in && i > 0) {
           const long long t0 = WV_CLK();
           while ((int)q.w != i) q = wv_ld_volatile_v4(slot);
           WV_DBG_ADD(4, WV_CLK() - t0);
-          if ((int)q.z != src_e || e != fin_e) { src_e = (int)q.z; fin_e = e; fin = pow2i(src_e - e); }
-          if (lane == 0) bxs = __hiloint2double((int)q.y, (int)q.x) * fin;
+          src_e = (int)q.z;
+          const double bin = __hiloint2double((int)q.y, (int)q.x) * pow2i(src_e - e);
+          if (lane == 0) bxs = bin;
         }
         {
           so[1] = fma(skipd[0], bxs, x[1] + x[0]);
@@ -391,15 +379,25 @@ __device__ void wave_lattice(const WaveParams& p, const WaveView& sv, int b, int
           vale0[(size_t)k * LANES] = BWD ? e : (apply ? en_next : e);
         }
         if (apply) { e = en_next; fb = fb_next; }
-        if (has_out && lane == 31)
-          wv_st_volatile_v4(bnd_out + (i & (RB - 1)),
-                            make_uint4((uint32_t)__double2loint(x[K - 1]), (uint32_t)__double2hiint(x[K - 1]), (uint32_t)e, (uint32_t)(i + 1)));
+        if (has_out)
+          wv_st_volatile_v4_if(bnd_out + (i & (RB - 1)),
+                               make_uint4((uint32_t)__double2loint(x[K - 1]), (uint32_t)__double2hiint(x[K - 1]), (uint32_t)e, (uint32_t)(i + 1)),
+                               lane == 31);
       }
     }
-    if (((i0 + G) & (CF - 1)) == 0 || i0 + G >= Ti) {
-      __syncwarp();
-      if (lane == 0) { __threadfence_block(); sv.ctl->lat_prog[w] = min(i0 + G, Ti); }
-    }
+    // publish the group (combiners and the ring owners poll these)
+    __syncwarp();
+    if (lane == 0) { __threadfence_block(); sv.ctl->lat_prog[w] = min(i0 + G, Ti); }
+  };
+
+  int i0 = 0;
+  for (; i0 + G <= Ti; i0 += G) {
+    if ((i0 & (CF - 1)) == 0) chunk_wait(i0);
+    group(std::true_type{}, i0);
+  }
+  if (i0 < Ti) {
+    if ((i0 & (CF - 1)) == 0) chunk_wait(i0);
+    group(std::false_type{}, i0);
   }
   WV_DBG_ADD(0, WV_CLK() - tstart);
   // exit cells S-1 and S-2 of the last frame: Z = their sum (ctc_loss.cpp:63-70)
@@ -417,6 +415,7 @@ __device__ void wave_combiner(const WaveParams& p, const WaveView& sv, int b, in
   const long long tstart = WV_CLK();
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int H = K / 2, LANES = 32 * NW, CELLS = LANES * K, ROWW = LANES * (K + 1), PF = kWavePF;
+  constexpr int SROW = ROWW + 4;   // staged row: the stashed row + a zero word (index ROWW) that cells past the lattice pair with
   constexpr int KLOG = K == 4 ? 2 : 3;
   const WaveLayout& L = p.L;
   const int NC = L.NC;
@@ -426,12 +425,12 @@ __device__ void wave_combiner(const WaveParams& p, const WaveView& sv, int b, in
   const int nstore_peer = Ti - nstore;
   auto frame_t = [&](int i) { return BWD ? (Ti - 1 - i) : i; };
   uint32_t* const stash_b = p.stash + (size_t)b * p.T * ROWW;
-  uint32_t* const stage = sv.stage + (size_t)q * PF * ROWW;
-  uint32_t* const acc = sv.acc + (size_t)q * L.vpad;
+  uint32_t* const stage = sv.stage + (size_t)q * PF * SROW;
+  uint32_t* const acc = sv.acc + (size_t)q * 4 * L.vpad;   // four interleaved copies per symbol (lane & 3): fewer same-address atomics
 
   auto wait_val = [&](int i) {
     const long long t0 = WV_CLK();
-    while (wv_min_prog<8>(sv.ctl->lat_prog, NW) <= i) __nanosleep(32);
+    while (wv_min_prog<8>(sv.ctl->lat_prog, NW) <= i) { if (L.nap) __nanosleep(L.nap); }
     __threadfence_block();
     WV_DBG_ADD(1, WV_CLK() - t0);
   };
@@ -441,7 +440,7 @@ __device__ void wave_combiner(const WaveParams& p, const WaveView& sv, int b, in
   };
   auto prefetch = [&](int i2, int slot) {   // the other sweep's stored row of my frame i2 -> staging slot
     if (i2 < Ti) {
-      uint32_t* dst = stage + (size_t)slot * ROWW;
+      uint32_t* dst = stage + (size_t)slot * SROW;
       const uint32_t* src = stash_b + (size_t)frame_t(i2) * ROWW;
       for (int u = lane; u < ROWW / 4; u += 32) wv_cp_async_cg16(dst + 4 * u, src + 4 * u);
     }
@@ -481,7 +480,8 @@ __device__ void wave_combiner(const WaveParams& p, const WaveView& sv, int b, in
   for (int u = 0; u < PF; u++) { prefetch(i + u * NC, u); wv_cp_async_commit(); }
 
   // Per lane: the lattice lanes g = lane + 32u it multiplies.  My cell m = g*K + j is the other sweep's cell
-  // mp = S-1-m (cells past S carry zero mass on my side, so a clamped index is enough there).
+  // mp = S-1-m: cells j <= r = (S-1) mod K of a lane sit in the other sweep's lane lA = mp0 >> KLOG, the rest in
+  // lA - 1, so a lane pairs with two block exponents.  Cells past the lattice (mp < 0) pair with the zero word.
   int mp0[NW];              // other-sweep index of my cell j = 0
   uint32_t* lcol[NW][H];    // accumulator of the label of cell j = 2h+1 (blank past L_i: receives zeros)
 #pragma unroll
@@ -489,8 +489,9 @@ __device__ void wave_combiner(const WaveParams& p, const WaveView& sv, int b, in
     const int g = lane + 32 * u;
     mp0[u] = S - 1 - g * K;
 #pragma unroll
-    for (int h = 0; h < H; h++) lcol[u][h] = acc + sv.lab[g * H + h];
+    for (int h = 0; h < H; h++) lcol[u][h] = acc + 4 * sv.lab[g * H + h] + (lane & 3);
   }
+  const int r = (S - 1) & (K - 1);
 
   bool have_z = false;
   double cz = 0.0;   // 2^31 / Z as mantissa in [1,2); its exponent is folded into Ez
@@ -499,12 +500,12 @@ __device__ void wave_combiner(const WaveParams& p, const WaveView& sv, int b, in
   for (int k = 0; i < Ti; i += NC, ++k) {
     wait_val(i);
     { const long long t0 = WV_CLK(); wv_cp_async_wait<PF - 1>(); __syncwarp(); WV_DBG_ADD(5, WV_CLK() - t0); }
-    const uint32_t* orow = stage + (size_t)(k % PF) * ROWW;
+    const uint32_t* orow = stage + (size_t)(k % PF) * SROW;
     const size_t ent0 = (size_t)(i & (L.RV - 1)) * LANES;
     const uint32_t* valw_row = sv.valw + ent0 * K;
     const int* vale_row = sv.vale + ent0;
     double pr[NW][K];
-    int El[NW][K];
+    int ElA[NW], ElB[NW];
 #pragma unroll
     for (int u = 0; u < NW; u++) {
       const int g = lane + 32 * u;
@@ -515,12 +516,13 @@ __device__ void wave_combiner(const WaveParams& p, const WaveView& sv, int b, in
         wd[4 * v] = t4.x; wd[4 * v + 1] = t4.y; wd[4 * v + 2] = t4.z; wd[4 * v + 3] = t4.w;
       }
       const int em = vale_row[g];
+      const int lA = mp0[u] >> KLOG;   // arithmetic shift: negative past the lattice
+      ElA[u] = em + (int)orow[CELLS + max(lA, 0)];
+      ElB[u] = em + (int)orow[CELLS + max(lA - 1, 0)];
 #pragma unroll
       for (int j = 0; j < K; j++) {
-        const int mpc = max(mp0[u] - j, 0);
-        // my cell S (the first one past the lattice) is nonzero BEFORE its emission in the backward sweep
-        pr[u][j] = mp0[u] >= j ? wv_hi2d(wd[j]) * wv_hi2d(orow[mpc]) : 0.0;
-        El[u][j] = em + (int)orow[CELLS + (mpc >> KLOG)];
+        const int mp = mp0[u] - j;
+        pr[u][j] = wv_hi2d(wd[j]) * wv_hi2d(orow[mp >= 0 ? mp : ROWW]);
       }
     }
     if (!have_z) {
@@ -529,20 +531,22 @@ __device__ void wave_combiner(const WaveParams& p, const WaveView& sv, int b, in
 #pragma unroll
       for (int u = 0; u < NW; u++)
 #pragma unroll
-        for (int j = 0; j < K; j++) if (pr[u][j] > 0.0) emax = max(emax, El[u][j]);
+        for (int j = 0; j < K; j++) if (pr[u][j] > 0.0) emax = max(emax, j <= r ? ElA[u] : ElB[u]);
       emax = warp_max_int(emax);
       double tot = 0.0;
 #pragma unroll
-      for (int u = 0; u < NW; u++)
+      for (int u = 0; u < NW; u++) {
+        const double fA = pow2i(ElA[u] - emax), fB = pow2i(ElB[u] - emax);
 #pragma unroll
-        for (int j = 0; j < K; j++) if (pr[u][j] > 0.0) tot += pr[u][j] * pow2i(El[u][j] - emax);
+        for (int j = 0; j < K; j++) if (pr[u][j] > 0.0) tot += pr[u][j] * (j <= r ? fA : fB);
+      }
       tot = warp_sum(tot);
       // 2^31 / Z = cz * 2^kz with cz in [1,2): the power of two moves into Ez, so the per-cell scale
       // 2^(El - Ez) * cz stays finite whatever stale exponent a massless lane carries (0 * finite = 0).
       // tot == 0 or NaN: the lattice tail flags the utterance and the block is overwritten with NaN.
-      const double r = 2147483648.0 / tot;
-      const int kz = ((__double2hiint(r) >> 20) & 0x7ff) - 1023;
-      cz = __hiloint2double((__double2hiint(r) & 0x800fffff) | 0x3ff00000, __double2loint(r));
+      const double rz = 2147483648.0 / tot;
+      const int kz = ((__double2hiint(rz) >> 20) & 0x7ff) - 1023;
+      cz = __hiloint2double((__double2hiint(rz) & 0x800fffff) | 0x3ff00000, __double2loint(rz));
       Ez = emax - kz;
       have_z = true;
     }
@@ -550,9 +554,10 @@ __device__ void wave_combiner(const WaveParams& p, const WaveView& sv, int b, in
     uint32_t bsum = 0u;
 #pragma unroll
     for (int u = 0; u < NW; u++) {
+      const double sA = pow2i(ElA[u] - Ez) * cz, sB = pow2i(ElB[u] - Ez) * cz;
 #pragma unroll
       for (int j = 0; j < K; j++) {
-        const uint32_t qv = __double2uint_rn(pr[u][j] * (pow2i(El[u][j] - Ez) * cz));
+        const uint32_t qv = __double2uint_rn(pr[u][j] * (j <= r ? sA : sB));
         if (j & 1) atomicAdd(lcol[u][j >> 1], qv);
         else bsum += qv;
       }
@@ -566,8 +571,9 @@ __device__ void wave_combiner(const WaveParams& p, const WaveView& sv, int b, in
       const float rs = (float)Erow[p.V + 1];
       const long long gbase = (long long)b * p.gsb + (long long)t * p.gst;
       for (int v = lane; v < p.V; v += 32) {
-        const uint32_t a = acc[v] + (v == p.blank ? qb : 0u);
-        acc[v] = 0u;
+        const uint4 a4 = reinterpret_cast<const uint4*>(acc)[v];
+        reinterpret_cast<uint4*>(acc)[v] = make_uint4(0u, 0u, 0u, 0u);
+        const uint32_t a = a4.x + a4.y + a4.z + a4.w + (v == p.blank ? qb : 0u);
         const float gv = sc * ((float)Erow[v] * rs - (float)a * (1.f / 2147483648.f));
         if (p.dtype == E2E_F32) reinterpret_cast<float*>(p.grads)[gbase + v] = gv;
         else if (p.dtype == E2E_BF16) reinterpret_cast<__nv_bfloat16*>(p.grads)[gbase + v] = __float2bfloat16_rn(gv);
@@ -681,6 +687,10 @@ ctc_wave_kernel(const WaveParams p) {
     uint32_t* z = reinterpret_cast<uint32_t*>(smem_raw + p.L.off_acc);
     const int n = (p.L.total - p.L.off_acc) >> 2;
     for (int k = tid; k < n; k += blockDim.x) z[k] = 0u;
+  }
+  for (int k = tid; k < p.L.NC * kWavePF; k += blockDim.x) {   // the zero word (+ padding) after each staged row
+    uint32_t* zw = sv.stage + (size_t)k * (LANES * (K + 1) + 4) + LANES * (K + 1);
+    zw[0] = 0u; zw[1] = 0u; zw[2] = 0u; zw[3] = 0u;
   }
   __syncthreads();
   if (tid < p.L.NC) sv.ctl->comb_done[tid] = tid;

@@ -19,6 +19,7 @@ PyTorch is used for device memory and streams only; every byte of arithmetic hap
 ``libe2e_ctc.so``.
 """
 import ctypes
+import os
 
 import torch
 
@@ -153,6 +154,22 @@ class _Problem:
         return torch.empty_strided(x.size(), x.stride(), dtype=x.dtype, device=x.device, pin_memory=pin)
 
 
+_PLAN_ENV = ("E2E_CTC_WAVE", "E2E_CTC_NO_FUSED", "E2E_CTC_LEGACY", "E2E_CTC_CELLS_PER_LANE", "E2E_CTC_LATTICE_WARPS",
+             "E2E_CTC_LATENCY_MODE", "E2E_CTC_WAVE_NW", "E2E_CTC_WAVE_K", "E2E_CTC_WAVE_NC")
+
+
+# only consulted when one of them was set at import time or E2E_CTC_TEST_ENV=1 (the test-suite toggles them
+# between calls); a production process never pays for the lookups
+_TEST_ENV = bool(os.environ.get("E2E_CTC_TEST_ENV")) or any(os.environ.get(k) is not None for k in _PLAN_ENV)
+
+
+def _plan_env():
+    """The testing / tuning environment switches that change the library's kernel plan (and with it the
+    workspace size): part of the workspace-size cache key."""
+    g = os.environ.get
+    return tuple(g(k) for k in _PLAN_ENV)
+
+
 def _require_cuda():
     if not torch.cuda.is_available():
         raise RuntimeError("end2end_b200 needs a CUDA device (sm_100a): the CTC engine has no CPU fallback")
@@ -166,6 +183,7 @@ class CTCLossEngine:
         self._L = _lib.load()
         self._host = {}
         self._ws_bytes = {}
+        self._scratch_bufs = {}
 
     # ------------------------------------------------------------------ reference contract ----
     def compute(self, logits, targets, logits_lengths, targets_lengths, from_logits=False):
@@ -180,7 +198,7 @@ class CTCLossEngine:
             pb = _Problem(self.blank_idx, logits, targets, logits_lengths, targets_lengths, from_logits, logits.device)
             losses = torch.empty(pb.B, dtype=logits.dtype, device=logits.device)
             grads = pb.new_grads()
-            ws = self._workspace(pb)
+            ws = self._scratch(pb)
             _lib.check(self._L.e2e_ctc_loss_fwd_bwd_device(
                 ctypes.byref(pb.desc), _ptr(pb.logits), _ptr(pb.targets), _ptr(pb.logits_lengths),
                 _ptr(pb.targets_lengths), _ptr(losses), _ptr(grads), _ptr(ws), ws.numel(), _stream(logits.device)))
@@ -204,7 +222,7 @@ class CTCLossEngine:
             grads = pb.new_grads()
             reduced = torch.empty((), dtype=logits.dtype, device=dev) if reduce_scale is not None else None
             pair = torch.empty(2, dtype=torch.float64, device=dev) if want_pair else None
-            ws = self._workspace(pb)
+            ws = self._scratch(pb)
             _lib.check(self._L.e2e_ctc_loss_step_device(
                 ctypes.byref(pb.desc), _ptr(pb.logits), _ptr(pb.targets), _ptr(pb.logits_lengths),
                 _ptr(pb.targets_lengths), _ptr(losses), _ptr(grads), float(grad_scale), _ptr(reduced), _ptr(pair),
@@ -290,7 +308,7 @@ class CTCLossEngine:
 
     # ------------------------------------------------------------------ internals --------------
     def _workspace(self, pb):
-        key = (pb.B, pb.T, pb.V, pb.Lmax, pb.desc.dtype)
+        key = (pb.B, pb.T, pb.V, pb.Lmax, pb.desc.dtype) + (_plan_env() if _TEST_ENV else ())
         n = self._ws_bytes.get(key)
         if n is None:
             n = self._L.e2e_ctc_loss_workspace_bytes(ctypes.byref(pb.desc))
@@ -298,6 +316,33 @@ class CTCLossEngine:
                 raise _lib.E2EError(2, self._L.e2e_last_error_string().decode("utf-8", "replace"))
             self._ws_bytes[key] = n
         return torch.empty(n, dtype=torch.uint8, device=pb.logits.device)
+
+    def _scratch(self, pb):
+        """Workspace of a call that is finished with it when the call's kernels are (the fused forward+backward
+        entry points): one buffer per (device, stream), grown on demand and reused, so a training loop does not
+        push a workspace-sized block through the caching allocator every step (interleaved with the live
+        gradient blocks that fragments it into cudaMalloc/cudaFree cycles).  Kernels of successive calls on one
+        stream are ordered, so the reuse is safe; other streams get their own buffer."""
+        if os.environ.get("E2E_CTC_NO_SCRATCH_CACHE"):
+            return self._workspace(pb)
+        dev = pb.logits.device
+        key = (dev.index, _raw_stream(dev.index if dev.index is not None else torch.cuda.current_device()))
+        need = self._ws_need(pb)
+        buf = self._scratch_bufs.get(key)
+        if buf is None or buf.numel() < need:
+            buf = torch.empty(need, dtype=torch.uint8, device=dev)
+            self._scratch_bufs[key] = buf
+        return buf
+
+    def _ws_need(self, pb):
+        key = (pb.B, pb.T, pb.V, pb.Lmax, pb.desc.dtype) + (_plan_env() if _TEST_ENV else ())
+        n = self._ws_bytes.get(key)
+        if n is None:
+            n = self._L.e2e_ctc_loss_workspace_bytes(ctypes.byref(pb.desc))
+            if n == 0:
+                raise _lib.E2EError(2, self._L.e2e_last_error_string().decode("utf-8", "replace"))
+            self._ws_bytes[key] = n
+        return n
 
     def _host_engine(self, device):
         h = self._host.get(device)

@@ -7,6 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+os.environ.setdefault("E2E_CTC_TEST_ENV", "1")   # tests toggle the kernel-plan switches between calls (engine._plan_env)
 os.environ.setdefault("OMP_NUM_THREADS", "8")  # unset, tiny torch CPU ops stall ~50 ms in this image
 
 

@@ -224,6 +224,86 @@ def test_every_lattice_shape_vs_oracle(e2e, fused):
                 assert_parity(g_gpu, g_ref[keep], what="K=%d grads" % K)
 
 
+# --------------------------------------------------------------------------------------------
+# the wave kernel (2-CTA cluster per utterance, wavefront of lattice warps): every variant forced
+# --------------------------------------------------------------------------------------------
+WAVE_VARIANTS = [(4, 1), (4, 2), (4, 4), (4, 8), (8, 8)]   # (cells per lane, lattice warps per sweep)
+
+
+@pytest.mark.parametrize("K,NW", WAVE_VARIANTS)
+def test_wave_kernel_every_shape_vs_oracle(e2e, K, NW):
+    """Target lengths spread over the variant's whole range (so the exit cells land on every lane/warp
+    edge, warps beyond the lattice idle, the mirrored backward sweep pairs cells across lanes), adjacent
+    repeats, ragged T incl. T_i = 1 and T_i == L + repeats (the only alignment), infeasible rows."""
+    cells = 32 * K * NW
+    Lcap = min((cells - 1) // 2, 330)
+    g = torch.Generator().manual_seed(100 + cells)
+    B, V = 24, 7
+    tl = torch.linspace(0, Lcap, B).long()
+    T_ = int(Lcap * 1.6) + 12
+    tg = torch.randint(1, V, (B, max(Lcap, 1)), generator=g)
+    tg[::3, 1::2] = tg[::3, 0:-1:2]                       # plenty of adjacent repeats
+    rep = torch.tensor([int((tg[b, 1:tl[b]] == tg[b, :max(int(tl[b]) - 1, 0)]).sum()) for b in range(B)])
+    ll = torch.randint(T_ // 2, T_ + 1, (B,), generator=g)
+    ll = torch.maximum(ll, tl + rep)                      # feasible ...
+    ll[1] = 1                                             # ... except a one-frame utterance with targets (infeasible)
+    ll[5] = tl[5] + rep[5]                                # exactly one alignment
+    ll[0] = 1                                             # L = 0, T = 1
+    ll[7] = max(int(tl[7] + rep[7]) - 1, 1)               # infeasible by one frame
+    x = torch.randn(B, T_, V, generator=g)
+    lp = torch.log_softmax(x, 2)
+    l_ref, g_ref = oracle.engine(0).compute(lp, tg, ll, tl)
+    env = {"E2E_CTC_WAVE": "1", "E2E_CTC_WAVE_NW": str(NW), "E2E_CTC_WAVE_K": str(K)}
+    for from_logits, inp in ((False, lp), (True, x)):
+        l_gpu, g_gpu = _with_env(env, lambda: e2e.CTCLossEngine(0).compute(inp.cuda(), *cuda(tg, ll, tl), from_logits=from_logits))
+        assert_parity(l_gpu, l_ref, what="wave K=%d NW=%d losses" % (K, NW))
+        g_exp = g_ref.clone()
+        if from_logits:      # d/d logits on valid frames equals softmax - posterior; padding frames are 0
+            for row, n in enumerate(ll.tolist()):
+                g_exp[row, n:] = 0
+                if not torch.isfinite(l_ref[row]):
+                    g_exp[row] = float("nan")
+        assert_parity(g_gpu, g_exp, what="wave K=%d NW=%d grads (from_logits=%s)" % (K, NW, from_logits))
+
+
+@pytest.mark.parametrize("scale", [1.0, 5.0, 12.0])
+def test_wave_kernel_peaky_and_dtypes(e2e, scale):
+    """Peaky emissions (the block exponents move tens of bits per frame and massless lanes must pick up the
+    front's scale), 16-bit logits, time-major strides, blank != 0, int32 index tensors."""
+    x, tg, ll, tl = oracle.make_inputs(6, 300, 29, 60, 140, 31, scale=scale)
+    blank = 3
+    tg = torch.where(tg == blank, torch.tensor(0), tg)
+    env = {"E2E_CTC_WAVE": "1"}
+    l_ref, g_ref = oracle.engine(blank).compute(torch.log_softmax(x, 2), tg, ll, tl)
+    x_tm = x.permute(1, 0, 2).contiguous().cuda()
+    l_gpu, g_gpu = _with_env(env, lambda: e2e.CTCLossEngine(blank).compute(
+        torch.log_softmax(x_tm, 2).permute(1, 0, 2), tg.int().cuda(), ll.int().cuda(), tl.int().cuda()))
+    assert_parity(l_gpu, l_ref, what="wave peaky x%g losses" % scale)
+    assert_parity(g_gpu, g_ref, what="wave peaky x%g grads" % scale)
+    for dt in (torch.bfloat16, torch.float16):
+        xh = x.to(dt)
+        lr, gr = oracle.engine(blank).compute(torch.log_softmax(xh.float(), 2), tg, ll, tl)
+        lg, gg = _with_env(env, lambda: e2e.CTCLossEngine(blank).compute(xh.cuda(), *cuda(tg, ll, tl), from_logits=True))
+        for row, n in enumerate(ll.tolist()):
+            gr[row, n:] = 0
+        tol = BF16_RTOL if dt == torch.bfloat16 else 2.0 ** -11
+        assert_parity(lg.float(), lr, rtol=tol, atol=tol, what="wave %s losses" % dt)
+        assert_parity(gg.float(), gr, rtol=tol, atol=tol, what="wave %s grads" % dt)
+
+
+def test_wave_kernel_is_the_default_for_latency_shapes(e2e):
+    """B <= 74 (both CTAs of every utterance resident) with <= 512 lattice cells runs the wave kernel; its
+    result equals the one-warp-per-sweep kernel's within the parity budget and is bitwise reproducible."""
+    x, tg, ll, tl = oracle.make_inputs(16, 200, 29, 40, 100, 17)
+    args = (x.cuda(), *cuda(tg, ll, tl))
+    l_w, g_w = e2e.CTCLossEngine(0).compute(*args, from_logits=True)
+    l_w2, g_w2 = e2e.CTCLossEngine(0).compute(*args, from_logits=True)
+    l_s, g_s = _with_env({"E2E_CTC_WAVE": "0"}, lambda: e2e.CTCLossEngine(0).compute(*args, from_logits=True))
+    assert torch.equal(l_w, l_w2) and torch.equal(g_w, g_w2)
+    assert_parity(l_w, l_s, what="wave vs sweep losses")
+    assert_parity(g_w, g_s, what="wave vs sweep grads")
+
+
 @pytest.mark.parametrize("fused", [True, False])
 def test_two_lattice_warps_long_targets(e2e, fused):
     """2L+1 > 1280 cells: two lattice warps per sweep exchange their boundary cells through shared memory."""
