@@ -369,6 +369,11 @@ struct e2e_ctc_engine {
   cudaStream_t stream = nullptr;
   e2e::DevBuf logits, grads, targets, in_len, tgt_len, losses, ws, decoded, decoded_len;
   uint64_t h2d = 0, d2h = 0;
+  // chunked host pipeline: copy-in stream, compute streams, copy-out stream, one event pair per chunk
+  static constexpr int kMaxChunks = 8, kComputeStreams = 4;
+  cudaStream_t s_in = nullptr, s_out = nullptr, s_comp[kComputeStreams] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_in[kMaxChunks] = {}, ev_comp[kMaxChunks] = {}, ev_free = nullptr;
+  bool pipe_ready = false;
 };
 
 using namespace e2e;
@@ -564,6 +569,13 @@ void e2e_ctc_engine_destroy(e2e_ctc_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
+  if (e->pipe_ready) {
+    cudaStreamSynchronize(e->s_out);
+    cudaStreamDestroy(e->s_in); cudaStreamDestroy(e->s_out);
+    for (cudaStream_t c : e->s_comp) cudaStreamDestroy(c);
+    for (int k = 0; k < e2e_ctc_engine::kMaxChunks; k++) { cudaEventDestroy(e->ev_in[k]); cudaEventDestroy(e->ev_comp[k]); }
+    cudaEventDestroy(e->ev_free);
+  }
   DevBuf* bufs[] = {&e->logits, &e->grads, &e->targets, &e->in_len, &e->tgt_len, &e->losses, &e->ws, &e->decoded, &e->decoded_len};
   for (DevBuf* b : bufs) b->release();
   delete e;
@@ -591,6 +603,23 @@ int e2e_ctc_engine_loss_host(e2e_ctc_engine* e, const e2e_ctc_desc* desc, const 
     set_error("host tensors must be dense (batch-major or time-major contiguous)");
     return E2E_ERR_INVALID_ARGUMENT;
   }
+  // The buffers are on the host: lengths and labels outside their legal range (undefined behaviour in the
+  // reference, forward_backward.cpp:38-52 indexes with them) are rejected here, before anything is enqueued.
+  {
+    auto idx = [](const void* q, int is64, size_t i) -> long long {
+      return is64 ? reinterpret_cast<const long long*>(q)[i] : (long long)reinterpret_cast<const int*>(q)[i];
+    };
+    const int l64 = d.lengths_itype == E2E_I64, t64 = d.targets_itype == E2E_I64;
+    for (int b = 0; b < d.batch; b++) {
+      const long long Ti = idx(logits_lengths, l64, (size_t)b), Li = idx(targets_lengths, l64, (size_t)b);
+      if (Ti < 1 || Ti > d.max_frames) { set_error("logits_lengths must be in [1, %d] (utterance %d: %lld)", d.max_frames, b, Ti); return E2E_ERR_LENGTHS; }
+      if (Li < 0 || Li > d.max_targets) { set_error("targets_lengths must be in [0, %d] (utterance %d: %lld)", d.max_targets, b, Li); return E2E_ERR_LENGTHS; }
+      for (long long i = 0; i < Li; i++) {
+        const long long v = idx(targets, t64, (size_t)b * d.max_targets + (size_t)i);
+        if (v < 0 || v >= d.alphabet) { set_error("target labels must be in [0, %d) (utterance %d, position %lld: %lld)", d.alphabet, b, i, v); return E2E_ERR_LENGTHS; }
+      }
+    }
+  }
   LossPlan p;
   if (!make_loss_plan(d, true, &p)) { set_error("no lattice configuration for max_targets=%d", d.max_targets); return E2E_ERR_UNSUPPORTED; }
   E2E_CUDA_TRY(cudaSetDevice(e->device));
@@ -599,23 +628,91 @@ int e2e_ctc_engine_loss_host(e2e_ctc_engine* e, const e2e_ctc_desc* desc, const 
   const size_t n_tgt = (size_t)d.batch * d.max_targets * (d.targets_itype == E2E_I64 ? 8 : 4);
   const size_t n_len = (size_t)d.batch * (d.lengths_itype == E2E_I64 ? 8 : 4);
   const size_t n_loss = (size_t)d.batch * es;
-  if ((rc = e->logits.ensure(n_log)) || (rc = e->grads.ensure(n_log)) || (rc = e->targets.ensure(n_tgt + 8)) ||
-      (rc = e->in_len.ensure(n_len)) || (rc = e->tgt_len.ensure(n_len)) || (rc = e->losses.ensure(n_loss)) ||
-      (rc = e->ws.ensure(p.total)))
-    return rc;
-  cudaStream_t s = e->stream;
-  E2E_CUDA_TRY(cudaMemcpyAsync(e->logits.p, logits, n_log, cudaMemcpyHostToDevice, s));
-  if (n_tgt) E2E_CUDA_TRY(cudaMemcpyAsync(e->targets.p, targets, n_tgt, cudaMemcpyHostToDevice, s));
-  E2E_CUDA_TRY(cudaMemcpyAsync(e->in_len.p, logits_lengths, n_len, cudaMemcpyHostToDevice, s));
-  E2E_CUDA_TRY(cudaMemcpyAsync(e->tgt_len.p, targets_lengths, n_len, cudaMemcpyHostToDevice, s));
-  rc = loss_fwd_bwd(d, p, e->logits.p, e->targets.p, e->in_len.p, e->tgt_len.p, e->losses.p, e->grads.p, 1.0,
-                    reinterpret_cast<char*>(e->ws.p), s);
-  if (rc != E2E_OK) return rc;
-  E2E_CUDA_TRY(cudaMemcpyAsync(losses, e->losses.p, n_loss, cudaMemcpyDeviceToHost, s));
-  E2E_CUDA_TRY(cudaMemcpyAsync(grads, e->grads.p, n_log, cudaMemcpyDeviceToHost, s));
-  E2E_CUDA_TRY(cudaStreamSynchronize(s));
   e->h2d = n_log + n_tgt + 2 * n_len;
   e->d2h = n_loss + n_log;
+
+  // Utterances are independent, so a batch-major batch is cut into chunks of utterances that flow through
+  // three stages on separate streams -- copy in, kernels, copy out -- and the PCIe transfers of one chunk
+  // overlap the kernels of another (both copy directions run at once).  Time-major host tensors (a chunk
+  // of utterances is not contiguous there) and small batches take the single-stream path.
+  const bool batch_major = d.logits_stride_b == (int64_t)d.max_frames * d.alphabet && d.logits_stride_t == d.alphabet &&
+                           d.grads_stride_b == d.logits_stride_b && d.grads_stride_t == d.logits_stride_t;
+  int nch = env_int("E2E_CTC_HOST_CHUNKS", -1);
+  if (nch < 0) nch = (int)(n_log / (768 * 1024));          // aim at chunks of >= 0.75 MB of logits
+  if (nch > e2e_ctc_engine::kMaxChunks) nch = e2e_ctc_engine::kMaxChunks;
+  if (nch > d.batch) nch = d.batch;
+  if (!batch_major || nch < 2) {
+    if ((rc = e->logits.ensure(n_log)) || (rc = e->grads.ensure(n_log)) || (rc = e->targets.ensure(n_tgt + 8)) ||
+        (rc = e->in_len.ensure(n_len)) || (rc = e->tgt_len.ensure(n_len)) || (rc = e->losses.ensure(n_loss)) ||
+        (rc = e->ws.ensure(p.total)))
+      return rc;
+    cudaStream_t s = e->stream;
+    E2E_CUDA_TRY(cudaMemcpyAsync(e->logits.p, logits, n_log, cudaMemcpyHostToDevice, s));
+    if (n_tgt) E2E_CUDA_TRY(cudaMemcpyAsync(e->targets.p, targets, n_tgt, cudaMemcpyHostToDevice, s));
+    E2E_CUDA_TRY(cudaMemcpyAsync(e->in_len.p, logits_lengths, n_len, cudaMemcpyHostToDevice, s));
+    E2E_CUDA_TRY(cudaMemcpyAsync(e->tgt_len.p, targets_lengths, n_len, cudaMemcpyHostToDevice, s));
+    rc = loss_fwd_bwd(d, p, e->logits.p, e->targets.p, e->in_len.p, e->tgt_len.p, e->losses.p, e->grads.p, 1.0,
+                      reinterpret_cast<char*>(e->ws.p), s);
+    if (rc != E2E_OK) return rc;
+    E2E_CUDA_TRY(cudaMemcpyAsync(losses, e->losses.p, n_loss, cudaMemcpyDeviceToHost, s));
+    E2E_CUDA_TRY(cudaMemcpyAsync(grads, e->grads.p, n_log, cudaMemcpyDeviceToHost, s));
+    E2E_CUDA_TRY(cudaStreamSynchronize(s));
+    return E2E_OK;
+  }
+
+  if (!e->pipe_ready) {
+    E2E_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+    E2E_CUDA_TRY(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+    for (cudaStream_t& c : e->s_comp) E2E_CUDA_TRY(cudaStreamCreateWithFlags(&c, cudaStreamNonBlocking));
+    for (int k = 0; k < e2e_ctc_engine::kMaxChunks; k++) {
+      E2E_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_in[k], cudaEventDisableTiming));
+      E2E_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_comp[k], cudaEventDisableTiming));
+    }
+    E2E_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_free, cudaEventDisableTiming));
+    e->pipe_ready = true;
+  }
+  // chunk plans (a chunk may pick a different kernel than the whole batch would) and workspace offsets
+  const int per = (d.batch + nch - 1) / nch;
+  nch = (d.batch + per - 1) / per;
+  LossPlan cp[e2e_ctc_engine::kMaxChunks];
+  e2e_ctc_desc cd[e2e_ctc_engine::kMaxChunks];
+  size_t ws_off[e2e_ctc_engine::kMaxChunks + 1];
+  ws_off[0] = 0;
+  for (int k = 0; k < nch; k++) {
+    cd[k] = d;
+    cd[k].batch = (k + 1) * per <= d.batch ? per : d.batch - k * per;
+    if (!make_loss_plan(cd[k], true, &cp[k])) { set_error("no lattice configuration for a chunk of the batch"); return E2E_ERR_UNSUPPORTED; }
+    ws_off[k + 1] = ws_off[k] + align256(cp[k].total);
+  }
+  if ((rc = e->logits.ensure(n_log)) || (rc = e->grads.ensure(n_log)) || (rc = e->targets.ensure(n_tgt + 8)) ||
+      (rc = e->in_len.ensure(n_len)) || (rc = e->tgt_len.ensure(n_len)) || (rc = e->losses.ensure(n_loss)) ||
+      (rc = e->ws.ensure(ws_off[nch])))
+    return rc;
+  const size_t row_b = (size_t)d.max_frames * d.alphabet * es;            // bytes of one utterance's logits
+  const size_t tg_b = (size_t)d.max_targets * (d.targets_itype == E2E_I64 ? 8 : 4);
+  const size_t len_b = d.lengths_itype == E2E_I64 ? 8 : 4;
+  if (n_tgt) E2E_CUDA_TRY(cudaMemcpyAsync(e->targets.p, targets, n_tgt, cudaMemcpyHostToDevice, e->s_in));
+  E2E_CUDA_TRY(cudaMemcpyAsync(e->in_len.p, logits_lengths, n_len, cudaMemcpyHostToDevice, e->s_in));
+  E2E_CUDA_TRY(cudaMemcpyAsync(e->tgt_len.p, targets_lengths, n_len, cudaMemcpyHostToDevice, e->s_in));
+  for (int k = 0; k < nch; k++) {
+    const size_t b0 = (size_t)k * per, nb = (size_t)cd[k].batch;
+    char* dl = reinterpret_cast<char*>(e->logits.p) + b0 * row_b;
+    char* dg = reinterpret_cast<char*>(e->grads.p) + b0 * row_b;
+    E2E_CUDA_TRY(cudaMemcpyAsync(dl, reinterpret_cast<const char*>(logits) + b0 * row_b, nb * row_b, cudaMemcpyHostToDevice, e->s_in));
+    E2E_CUDA_TRY(cudaEventRecord(e->ev_in[k], e->s_in));
+    cudaStream_t sc = e->s_comp[k % e2e_ctc_engine::kComputeStreams];
+    E2E_CUDA_TRY(cudaStreamWaitEvent(sc, e->ev_in[k], 0));
+    rc = loss_fwd_bwd(cd[k], cp[k], dl, reinterpret_cast<char*>(e->targets.p) + b0 * tg_b,
+                      reinterpret_cast<char*>(e->in_len.p) + b0 * len_b, reinterpret_cast<char*>(e->tgt_len.p) + b0 * len_b,
+                      reinterpret_cast<char*>(e->losses.p) + b0 * es, dg, 1.0, reinterpret_cast<char*>(e->ws.p) + ws_off[k], sc);
+    if (rc != E2E_OK) { cudaDeviceSynchronize(); return rc; }
+    E2E_CUDA_TRY(cudaEventRecord(e->ev_comp[k], sc));
+    E2E_CUDA_TRY(cudaStreamWaitEvent(e->s_out, e->ev_comp[k], 0));
+    E2E_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(grads) + b0 * row_b, dg, nb * row_b, cudaMemcpyDeviceToHost, e->s_out));
+    E2E_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(losses) + b0 * es, reinterpret_cast<char*>(e->losses.p) + b0 * es, nb * es,
+                                 cudaMemcpyDeviceToHost, e->s_out));
+  }
+  E2E_CUDA_TRY(cudaStreamSynchronize(e->s_out));
   return E2E_OK;
 }
 

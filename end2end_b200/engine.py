@@ -92,7 +92,7 @@ def _dense3(x):
 class _Problem:
     """Validated, device-resident view of one batch plus the C descriptor."""
 
-    def __init__(self, blank_idx, logits, targets, logits_lengths, targets_lengths, from_logits, device):
+    def __init__(self, blank_idx, logits, targets, logits_lengths, targets_lengths, from_logits, device, validate=True):
         if logits.dim() != 3:
             raise ValueError("logits must be [batch, frames, alphabet], got %s" % (tuple(logits.shape),))
         if logits.dtype not in _DTYPES:
@@ -113,7 +113,7 @@ class _Problem:
             raise NotImplementedError("this build supports target length <= %d and alphabet <= %d"
                                       % (lim.max_targets, lim.max_alphabet))
         # the reference has undefined behaviour on these; reject when it costs no device sync
-        if not logits_lengths.is_cuda and not targets_lengths.is_cuda:
+        if validate and not logits_lengths.is_cuda and not targets_lengths.is_cuda:
             ll, tl = logits_lengths.to(torch.int64), targets_lengths.to(torch.int64)
             if bool((ll < 1).any()) or bool((ll > T).any()):
                 raise ValueError("logits_lengths must be in [1, %d]" % T)
@@ -356,16 +356,23 @@ class CTCLossEngine:
         cpu = torch.device("cpu")
         if not (logits.is_contiguous() or logits.permute(1, 0, 2).is_contiguous()):
             logits = logits.contiguous()
-        pb = _Problem(self.blank_idx, logits, targets, logits_lengths, targets_lengths, from_logits, cpu)
+        # lengths and labels are range-checked by the library's host entry point (plain loops over the host
+        # buffers) instead of a handful of small torch ops here
+        pb = _Problem(self.blank_idx, logits, targets, logits_lengths, targets_lengths, from_logits, cpu, validate=False)
         if pb.Lmax > 0 and not pb.targets.is_contiguous():
             pb.targets = pb.targets.contiguous()
             pb.desc.targets_stride_b = pb.Lmax
         losses = torch.empty(pb.B, dtype=logits.dtype, pin_memory=True)
         grads = pb.new_grads(pin=True)
         h = self._host_engine(dev)
-        _lib.check(self._L.e2e_ctc_engine_loss_host(
-            h.handle, ctypes.byref(pb.desc), _ptr(pb.logits), _ptr(pb.targets), _ptr(pb.logits_lengths),
-            _ptr(pb.targets_lengths), _ptr(losses), _ptr(grads)))
+        try:
+            _lib.check(self._L.e2e_ctc_engine_loss_host(
+                h.handle, ctypes.byref(pb.desc), _ptr(pb.logits), _ptr(pb.targets), _ptr(pb.logits_lengths),
+                _ptr(pb.targets_lengths), _ptr(losses), _ptr(grads)))
+        except _lib.E2EError as err:
+            if err.code == _lib.E2E_ERR_LENGTHS:
+                raise ValueError(str(err)) from None
+            raise
         return losses, grads
 
     def last_host_traffic(self):
