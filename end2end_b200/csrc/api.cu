@@ -181,7 +181,7 @@ static bool make_wave_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   if (!K) return false;
   WaveLayout L;
   L.K = K; L.NW = NW;
-  L.NC = env_int("E2E_CTC_WAVE_NC", NW >= 4 ? 4 : 2);
+  L.NC = env_int("E2E_CTC_WAVE_NC", NW >= 4 ? 6 : 2);
   L.NP = env_int("E2E_CTC_WAVE_NP", NW >= 4 ? 2 : 1);
   if (L.NC < 1 || L.NC > 8 || (L.NP != 1 && L.NP != 2 && L.NP != 4)) return false;
   L.nap = env_int("E2E_CTC_WAVE_NAP", 32);
@@ -205,11 +205,12 @@ static bool make_wave_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   if (L.RV < kWaveCF || (L.RV & (L.RV - 1))) return false;
   size_t off = 0;
   L.off_lab = 0; off = (size_t)align16i((size_t)(lanes * K / 2 + 1) * 4);
+  L.off_occ = (int)off; off = (size_t)align16i(off + (size_t)(lanes * K / 2 + d.alphabet + 2) * 4);   // label indices by symbol + offsets
   L.off_E = (int)off; off = (size_t)align16i(off + (size_t)L.R * L.es * 8);
   L.off_valw = (int)off; off += (size_t)L.RV * lanes * K * 4;
   L.off_vale = (int)off; off += (size_t)L.RV * lanes * 4;
   L.off_stage = (int)off; off += (size_t)L.NC * kWavePF * (roww + 4) * 4;
-  L.off_acc = (int)off; off += (size_t)L.NC * 4 * L.vpad * 4;
+  L.off_acc = (int)off; off += (size_t)L.NC * (lanes * K / 2 + 4) * 4;   // one row of label posteriors per combiner warp (+ a spare slot)
   L.off_bnd = (int)off; off += (size_t)NW * kWaveRB * 16;
   L.off_ctl = (int)off; off += wave_ctl_bytes();
   L.total = (int)off;

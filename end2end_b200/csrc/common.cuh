@@ -47,7 +47,7 @@ struct WaveLayout {
   int R, RV;        // frames in the emission ring / in the val ring (powers of two)
   int es;           // doubles per emission-ring frame: V symbols, a zero column, the row normaliser
   int vpad;         // u32 posterior accumulators per combiner warp
-  int off_lab, off_E, off_valw, off_vale, off_stage, off_acc, off_bnd, off_ctl, total;
+  int off_lab, off_occ, off_E, off_valw, off_vale, off_stage, off_acc, off_bnd, off_ctl, total;
 };
 
 // One forward call leaves everything the backward needs in the caller's workspace.

@@ -56,7 +56,8 @@ struct WaveCtl {
   volatile int lat_prog[8];      // lattice warp w: frames [0, value) swept and dropped into the val ring
   volatile int comb_done[8];     // combiner q: the next frame it will take (all its earlier frames are done)
   int zero;                      // no path survives / NaN input
-  int misc[3];
+  volatile int occ_ready;        // the label occurrence lists (CSR by symbol) are built
+  int misc[2];
   double tail_x[2]; int tail_e[2]; int tail_on[2];
   double lse[4];
 };
@@ -105,16 +106,17 @@ __device__ __forceinline__ double wv_emission(float x, float m, float ls, int fr
 }
 
 struct WaveView {
-  int* lab; double* E; uint32_t* valw; int* vale; uint32_t* stage; uint32_t* acc; uint4* bnd; WaveCtl* ctl;
+  int* lab; int* occ; double* E; uint32_t* valw; int* vale; uint32_t* stage; float* post; uint4* bnd; WaveCtl* ctl;
 };
 __device__ __forceinline__ WaveView wv_carve(unsigned char* base, const WaveLayout& L) {
   WaveView v;
   v.lab = reinterpret_cast<int*>(base + L.off_lab);
+  v.occ = reinterpret_cast<int*>(base + L.off_occ);
   v.E = reinterpret_cast<double*>(base + L.off_E);
   v.valw = reinterpret_cast<uint32_t*>(base + L.off_valw);
   v.vale = reinterpret_cast<int*>(base + L.off_vale);
   v.stage = reinterpret_cast<uint32_t*>(base + L.off_stage);
-  v.acc = reinterpret_cast<uint32_t*>(base + L.off_acc);
+  v.post = reinterpret_cast<float*>(base + L.off_acc);
   v.bnd = reinterpret_cast<uint4*>(base + L.off_bnd);
   v.ctl = reinterpret_cast<WaveCtl*>(base + L.off_ctl);
   return v;
@@ -258,21 +260,24 @@ __device__ void wave_lattice(const WaveParams& p, const WaveView& sv, int b, int
   uint4* const bnd_out = sv.bnd + (size_t)w * RB;
 
   auto chunk_wait = [&](int i0) {
-    const int c = i0 / CF;
-    const long long t0 = WV_CLK();
+    // one optimistic pass with all the progress words in flight together; the slow loops only when one is behind
     const int bi = i0 / kWavePB;   // the producer block the chunk belongs to
     const volatile int* er = &sv.ctl->e_ready[bi & (L.NP - 1)];
-    while (*er <= bi) {}
-    const long long t1 = WV_CLK();
-    const int needv = i0 + CF - L.RV;
-    if (needv > 0) { while (wv_min_prog<8>(sv.ctl->comb_done, L.NC) < needv) {} }
-    const long long t2 = WV_CLK();
-    if (has_out) {
-      const int needb = i0 + CF - RB + 1;   // the slots this chunk overwrites have been read
-      if (needb > 0) { while (sv.ctl->lat_prog[w + 1] < needb) {} }
+    const int needv = i0 + CF - L.RV;        // frames below this have left the val ring
+    const int needb = i0 + CF - RB + 1;      // the boundary slots this chunk overwrites have been read
+    const int ev = *er;
+    const int cm = wv_min_prog<8>(sv.ctl->comb_done, L.NC);
+    const int lp = has_out ? sv.ctl->lat_prog[w + 1] : 0x7fffffff;
+    if (ev <= bi || cm < needv || lp < needb) {
+      const long long t0 = WV_CLK();
+      while (*er <= bi) {}
+      const long long t1 = WV_CLK();
+      while (wv_min_prog<8>(sv.ctl->comb_done, L.NC) < needv) {}
+      const long long t2 = WV_CLK();
+      if (has_out) { while (sv.ctl->lat_prog[w + 1] < needb) {} }
+      WV_DBG_ADD(1, t1 - t0); WV_DBG_ADD(2, t2 - t1); WV_DBG_ADD(3, WV_CLK() - t2);
     }
     __threadfence_block();
-    WV_DBG_ADD(1, t1 - t0); WV_DBG_ADD(2, t2 - t1); WV_DBG_ADD(3, WV_CLK() - t2);
   };
 
   // One group of G frames.  FULLG (all G frames exist): the boundary slots of the whole group are fetched up
@@ -426,7 +431,9 @@ __device__ void wave_combiner(const WaveParams& p, const WaveView& sv, int b, in
   auto frame_t = [&](int i) { return BWD ? (Ti - 1 - i) : i; };
   uint32_t* const stash_b = p.stash + (size_t)b * p.T * ROWW;
   uint32_t* const stage = sv.stage + (size_t)q * PF * SROW;
-  uint32_t* const acc = sv.acc + (size_t)q * 4 * L.vpad;   // four interleaved copies per symbol (lane & 3): fewer same-address atomics
+  float* const post = sv.post + (size_t)q * (LANES * H + 4);   // this warp's label posteriors of one frame, grouped by symbol
+  int* const rank = sv.occ;                                    // label index -> its slot in that grouping ...
+  int* const ofs = sv.occ + LANES * H;                         // ... symbol v owns slots [ofs[v], ofs[v+1])
 
   auto wait_val = [&](int i) {
     const long long t0 = WV_CLK();
@@ -445,6 +452,30 @@ __device__ void wave_combiner(const WaveParams& p, const WaveView& sv, int b, in
       for (int u = lane; u < ROWW / 4; u += 32) wv_cp_async_cg16(dst + 4 * u, src + 4 * u);
     }
   };
+
+  if (q == 0) {
+    // Occurrence lists of the utterance's labels by symbol (a counting sort, built once while the first frames
+    // are swept): the gradient row then GATHERS the posteriors of a symbol's label cells in a fixed order --
+    // no shared-memory atomics, and the sum is bitwise reproducible.
+    int base = 0;
+    for (int v0 = 0; v0 < p.V; v0 += 32) {
+      const int v = v0 + lane;
+      int c = 0;
+      if (v < p.V) for (int li = 0; li < Li; li++) c += (sv.lab[li] == v);
+      int inc = c;   // inclusive scan over the 32 symbols of this pass
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+      int k = base + inc - c;
+      if (v < p.V) {
+        ofs[v] = k;
+        for (int li = 0; li < Li; li++) if (sv.lab[li] == v) rank[li] = k++;
+      }
+      base += __shfl_sync(FULL, inc, 31);
+    }
+    if (lane == 0) ofs[p.V] = base;
+    __syncwarp();
+    if (lane == 0) { __threadfence_block(); sv.ctl->occ_ready = 1; }
+  }
 
   int i = q;
   // ---- first half: val ring -> global stash ----
@@ -474,6 +505,8 @@ __device__ void wave_combiner(const WaveParams& p, const WaveView& sv, int b, in
     const int want = min(NC, nstore_peer);
     const int* flag = p.meet + 2 * b + (BWD ? 0 : 1);
     while (wv_ld_acquire_gpu(flag) < want) __nanosleep(64);
+    while (sv.ctl->occ_ready == 0) __nanosleep(64);
+    __threadfence_block();
   }
   WV_DBG_ADD(4, WV_CLK() - tmeet);
   const long long tsecond = WV_CLK();
@@ -483,13 +516,13 @@ __device__ void wave_combiner(const WaveParams& p, const WaveView& sv, int b, in
   // mp = S-1-m: cells j <= r = (S-1) mod K of a lane sit in the other sweep's lane lA = mp0 >> KLOG, the rest in
   // lA - 1, so a lane pairs with two block exponents.  Cells past the lattice (mp < 0) pair with the zero word.
   int mp0[NW];              // other-sweep index of my cell j = 0
-  uint32_t* lcol[NW][H];    // accumulator of the label of cell j = 2h+1 (blank past L_i: receives zeros)
+  int slot[NW][H];          // where the posterior of label cell j = 2h+1 goes (a spare slot past L_i)
 #pragma unroll
   for (int u = 0; u < NW; u++) {
     const int g = lane + 32 * u;
     mp0[u] = S - 1 - g * K;
 #pragma unroll
-    for (int h = 0; h < H; h++) lcol[u][h] = acc + 4 * sv.lab[g * H + h] + (lane & 3);
+    for (int h = 0; h < H; h++) slot[u][h] = g * H + h < Li ? rank[g * H + h] : LANES * H;
   }
   const int r = (S - 1) & (K - 1);
 
@@ -550,31 +583,40 @@ __device__ void wave_combiner(const WaveParams& p, const WaveView& sv, int b, in
       Ez = emax - kz;
       have_z = true;
     }
-    // posteriors summed per symbol: fixed point 2^-31 (the sum per symbol is <= 1), integer adds commute
+    // posteriors scaled by 2^31: blank cells are summed as fixed point (one warp-wide integer add), label
+    // cells go to this warp's row by label index
     uint32_t bsum = 0u;
 #pragma unroll
     for (int u = 0; u < NW; u++) {
       const double sA = pow2i(ElA[u] - Ez) * cz, sB = pow2i(ElB[u] - Ez) * cz;
 #pragma unroll
       for (int j = 0; j < K; j++) {
-        const uint32_t qv = __double2uint_rn(pr[u][j] * (j <= r ? sA : sB));
-        if (j & 1) atomicAdd(lcol[u][j >> 1], qv);
-        else bsum += qv;
+        const double pv = pr[u][j] * (j <= r ? sA : sB);
+        if (j & 1) post[slot[u][j >> 1]] = (float)pv;
+        else bsum += __double2uint_rn(pv);
       }
     }
     const uint32_t qb = __reduce_add_sync(FULL, bsum);
     __syncwarp();
-    // gradient row: scale * (softmax - posterior); log-prob input: exp(lp) - posterior (the engine contract)
+    // gradient row: scale * (softmax - posterior); log-prob input: exp(lp) - posterior (the engine contract).
+    // A lane sums the posteriors of its symbol's label cells in list order.
     {
       const int t = frame_t(i);
       const double* Erow = sv.E + (size_t)(i & (L.R - 1)) * L.es;
       const float rs = (float)Erow[p.V + 1];
       const long long gbase = (long long)b * p.gsb + (long long)t * p.gst;
       for (int v = lane; v < p.V; v += 32) {
-        const uint4 a4 = reinterpret_cast<const uint4*>(acc)[v];
-        reinterpret_cast<uint4*>(acc)[v] = make_uint4(0u, 0u, 0u, 0u);
-        const uint32_t a = a4.x + a4.y + a4.z + a4.w + (v == p.blank ? qb : 0u);
-        const float gv = sc * ((float)Erow[v] * rs - (float)a * (1.f / 2147483648.f));
+        // the symbol's label cells are contiguous in the row: four independent partial sums, fixed order
+        float a0 = v == p.blank ? (float)qb : 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const int k1 = ofs[v + 1];
+        for (int kk = ofs[v]; kk < k1; kk += 4) {
+          a0 += post[kk];
+          a1 += kk + 1 < k1 ? post[kk + 1] : 0.f;
+          a2 += kk + 2 < k1 ? post[kk + 2] : 0.f;
+          a3 += kk + 3 < k1 ? post[kk + 3] : 0.f;
+        }
+        const float a = (a0 + a1) + (a2 + a3);
+        const float gv = sc * ((float)Erow[v] * rs - a * (1.f / 2147483648.f));
         if (p.dtype == E2E_F32) reinterpret_cast<float*>(p.grads)[gbase + v] = gv;
         else if (p.dtype == E2E_BF16) reinterpret_cast<__nv_bfloat16*>(p.grads)[gbase + v] = __float2bfloat16_rn(gv);
         else reinterpret_cast<__half*>(p.grads)[gbase + v] = __float2half_rn(gv);

@@ -67,6 +67,17 @@ class _ShardedLossFunction(Function):
         known = float(global_batch) if global_batch is not None else None
         ctx.folded = 1.0 / known if (mean and known) else 1.0     # constant part of grad_output baked into the kernel
         ctx.on_device = logits.is_cuda
+        reducing = group is not False and dist.is_available() and dist.is_initialized()
+        if logits.is_cuda and need_grad and (known or not mean):
+            # fast path (the global batch is known, or the loss is a plain sum): the reduce kernel already
+            # leaves scale * sum(local losses) as a 0-dim tensor of the logits dtype; that scalar IS the
+            # all-reduce buffer and the result -- no host-side arithmetic around the collective
+            _, ctx.grads, total, _ = engine.step(logits, targets, logits_lengths, targets_lengths, from_logits,
+                                                 grad_scale=ctx.folded, reduce_scale=ctx.folded)
+            if reducing:
+                dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)   # THE collective of this path
+            ctx.inv_n = ctx.folded if mean else None
+            return total
         if logits.is_cuda and need_grad:
             _, ctx.grads, _, pair = engine.step(logits, targets, logits_lengths, targets_lengths, from_logits,
                                                 grad_scale=ctx.folded, want_pair=True)
@@ -78,7 +89,7 @@ class _ShardedLossFunction(Function):
             losses, grads = engine.compute(logits, targets, logits_lengths, targets_lengths, from_logits)
             ctx.grads = grads if need_grad else None
             pair = torch.stack([losses.double().sum(), torch.tensor(float(B), dtype=torch.float64)])
-        if group is not False and dist.is_available() and dist.is_initialized():
+        if reducing:
             dist.all_reduce(pair, op=dist.ReduceOp.SUM, group=group)   # THE collective of this path
         ctx.inv_n = None
         if mean:
