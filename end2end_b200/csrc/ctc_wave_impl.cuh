@@ -89,6 +89,15 @@ __device__ __forceinline__ int wv_ld_acquire_gpu(const int* p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
   return r;
 }
+// progress words: release stores / acquire loads at CTA scope (lighter than a fence around a volatile access)
+__device__ __forceinline__ void wv_st_release(volatile int* p, int v) {
+  asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(wv_smem_u32(const_cast<int*>(p))), "r"(v) : "memory");
+}
+__device__ __forceinline__ int wv_ld_acquire(const volatile int* p) {
+  int r;
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(r) : "r"(wv_smem_u32(const_cast<int*>(p))) : "memory");
+  return r;
+}
 __device__ __forceinline__ double wv_hi2d(uint32_t h) { return __hiloint2double((int)h, 0); }
 
 // p(t, v) relative to the row's log-sum-exp, as a double: the exponent argument is formed as torch's fp32
@@ -132,9 +141,9 @@ __device__ __forceinline__ WaveView wv_carve(unsigned char* base, const WaveLayo
 
 template <int N>
 __device__ __forceinline__ int wv_min_prog(const volatile int* a, int n) {
-  int m = a[0];
+  int m = wv_ld_acquire(a);
 #pragma unroll
-  for (int k = 1; k < N; k++) if (k < n) m = min(m, a[k]);
+  for (int k = 1; k < N; k++) if (k < n) m = min(m, wv_ld_acquire(a + k));
   return m;
 }
 
@@ -204,13 +213,12 @@ __device__ void wave_producer(const WaveParams& p, const WaveView& sv, int b, in
     if (need > 0) {
       const long long t0 = WV_CLK();
       while (wv_min_prog<8>(sv.ctl->lat_prog, NW) < need || wv_min_prog<8>(sv.ctl->comb_done, L.NC) < need) { if (L.nap) __nanosleep(L.nap); }
-      __threadfence_block();
       WV_DBG_ADD(1, WV_CLK() - t0);
     }
     if (p.V <= 32) lse += wave_produce_block<true>(p, sv, xbase, Ti, bi * PB, lane, BWD);
     else lse += wave_produce_block<false>(p, sv, xbase, Ti, bi * PB, lane, BWD);
     __syncwarp();
-    if (lane == 0) { __threadfence_block(); sv.ctl->e_ready[pw] = bi + 1; }
+    if (lane == 0) wv_st_release(&sv.ctl->e_ready[pw], bi + 1);
   }
   lse = warp_sum(lse);   // fixed order: deterministic loss for log-prob input
   if (lane == 0) sv.ctl->lse[pw] = lse;
@@ -265,19 +273,18 @@ __device__ void wave_lattice(const WaveParams& p, const WaveView& sv, int b, int
     const volatile int* er = &sv.ctl->e_ready[bi & (L.NP - 1)];
     const int needv = i0 + CF - L.RV;        // frames below this have left the val ring
     const int needb = i0 + CF - RB + 1;      // the boundary slots this chunk overwrites have been read
-    const int ev = *er;
+    const int ev = wv_ld_acquire(er);
     const int cm = wv_min_prog<8>(sv.ctl->comb_done, L.NC);
-    const int lp = has_out ? sv.ctl->lat_prog[w + 1] : 0x7fffffff;
+    const int lp = has_out ? wv_ld_acquire(&sv.ctl->lat_prog[w + 1]) : 0x7fffffff;
     if (ev <= bi || cm < needv || lp < needb) {
       const long long t0 = WV_CLK();
-      while (*er <= bi) {}
+      while (wv_ld_acquire(er) <= bi) {}
       const long long t1 = WV_CLK();
       while (wv_min_prog<8>(sv.ctl->comb_done, L.NC) < needv) {}
       const long long t2 = WV_CLK();
-      if (has_out) { while (sv.ctl->lat_prog[w + 1] < needb) {} }
+      if (has_out) { while (wv_ld_acquire(&sv.ctl->lat_prog[w + 1]) < needb) {} }
       WV_DBG_ADD(1, t1 - t0); WV_DBG_ADD(2, t2 - t1); WV_DBG_ADD(3, WV_CLK() - t2);
     }
-    __threadfence_block();
   };
 
   // One group of G frames.  FULLG (all G frames exist): the boundary slots of the whole group are fetched up
@@ -392,7 +399,7 @@ __device__ void wave_lattice(const WaveParams& p, const WaveView& sv, int b, int
     }
     // publish the group (combiners and the ring owners poll these)
     __syncwarp();
-    if (lane == 0) { __threadfence_block(); sv.ctl->lat_prog[w] = min(i0 + G, Ti); }
+    if (lane == 0) wv_st_release(&sv.ctl->lat_prog[w], min(i0 + G, Ti));
   };
 
   int i0 = 0;
@@ -438,12 +445,11 @@ __device__ void wave_combiner(const WaveParams& p, const WaveView& sv, int b, in
   auto wait_val = [&](int i) {
     const long long t0 = WV_CLK();
     while (wv_min_prog<8>(sv.ctl->lat_prog, NW) <= i) { if (L.nap) __nanosleep(L.nap); }
-    __threadfence_block();
     WV_DBG_ADD(1, WV_CLK() - t0);
   };
   auto done = [&](int i) {
     __syncwarp();
-    if (lane == 0) { __threadfence_block(); sv.ctl->comb_done[q] = i + NC; }
+    if (lane == 0) wv_st_release(&sv.ctl->comb_done[q], i + NC);
   };
   auto prefetch = [&](int i2, int slot) {   // the other sweep's stored row of my frame i2 -> staging slot
     if (i2 < Ti) {
@@ -474,7 +480,7 @@ __device__ void wave_combiner(const WaveParams& p, const WaveView& sv, int b, in
     }
     if (lane == 0) ofs[p.V] = base;
     __syncwarp();
-    if (lane == 0) { __threadfence_block(); sv.ctl->occ_ready = 1; }
+    if (lane == 0) wv_st_release(&sv.ctl->occ_ready, 1);
   }
 
   int i = q;
@@ -505,8 +511,7 @@ __device__ void wave_combiner(const WaveParams& p, const WaveView& sv, int b, in
     const int want = min(NC, nstore_peer);
     const int* flag = p.meet + 2 * b + (BWD ? 0 : 1);
     while (wv_ld_acquire_gpu(flag) < want) __nanosleep(64);
-    while (sv.ctl->occ_ready == 0) __nanosleep(64);
-    __threadfence_block();
+    while (wv_ld_acquire(&sv.ctl->occ_ready) == 0) __nanosleep(64);
   }
   WV_DBG_ADD(4, WV_CLK() - tmeet);
   const long long tsecond = WV_CLK();
