@@ -149,6 +149,34 @@ class _Problem:
         self.desc = d
         self.workspace = None
 
+    _FAST = {}
+
+    @classmethod
+    def make(cls, blank_idx, logits, targets, logits_lengths, targets_lengths, from_logits, device):
+        """``_Problem(...)`` with a cache: when every tensor already lives on ``device`` the checks depend only
+        on shapes / strides / dtypes, so a training loop (same layout every step) validates once and reuses
+        the C descriptor."""
+        if not (targets.is_cuda and logits_lengths.is_cuda and targets_lengths.is_cuda):
+            return cls(blank_idx, logits, targets, logits_lengths, targets_lengths, from_logits, device)
+        key = (logits.shape, logits.stride(), logits.dtype, targets.shape, targets.stride(), targets.dtype,
+               logits_lengths.dtype, logits_lengths.stride(), targets_lengths.dtype, targets_lengths.stride(),
+               targets.device, logits_lengths.device, targets_lengths.device, device, bool(from_logits), blank_idx)
+        hit = cls._FAST.get(key)
+        if hit is None:
+            pb = cls(blank_idx, logits, targets, logits_lengths, targets_lengths, from_logits, device)
+            same = (pb.logits is logits and pb.targets is targets and pb.logits_lengths is logits_lengths and
+                    pb.targets_lengths is targets_lengths)
+            if same:                      # nothing had to be converted or copied: the layout is reusable as is
+                if len(cls._FAST) > 256:
+                    cls._FAST.clear()
+                cls._FAST[key] = (pb.desc, pb.B, pb.T, pb.V, pb.Lmax)
+            return pb
+        pb = cls.__new__(cls)
+        pb.logits, pb.targets, pb.logits_lengths, pb.targets_lengths = logits, targets, logits_lengths, targets_lengths
+        pb.desc, pb.B, pb.T, pb.V, pb.Lmax = hit
+        pb.workspace = None
+        return pb
+
     def new_grads(self, pin=False):
         x = self.logits
         return torch.empty_strided(x.size(), x.stride(), dtype=x.dtype, device=x.device, pin_memory=pin)
@@ -184,6 +212,7 @@ class CTCLossEngine:
         self._host = {}
         self._ws_bytes = {}
         self._scratch_bufs = {}
+        self._scale_desc = {}
 
     # ------------------------------------------------------------------ reference contract ----
     def compute(self, logits, targets, logits_lengths, targets_lengths, from_logits=False):
@@ -217,7 +246,7 @@ class CTCLossEngine:
         logits = logits.detach()
         dev = logits.device
         with _on_device(dev):
-            pb = _Problem(self.blank_idx, logits, targets, logits_lengths, targets_lengths, from_logits, dev)
+            pb = _Problem.make(self.blank_idx, logits, targets, logits_lengths, targets_lengths, from_logits, dev)
             losses = torch.empty(pb.B, dtype=logits.dtype, device=dev)
             grads = pb.new_grads()
             reduced = torch.empty((), dtype=logits.dtype, device=dev) if reduce_scale is not None else None
@@ -233,15 +262,23 @@ class CTCLossEngine:
         """``grads[b] *= grad_output[b or 0]`` in place (functions/forward_backward.py:34); utterances whose
         factor is exactly 1 are skipped on the device."""
         dev = grads.device
-        g = grad_output.detach().to(device=dev, dtype=grads.dtype).contiguous()
+        g = grad_output.detach()
+        if g.device != dev or g.dtype != grads.dtype or not g.is_contiguous():
+            g = g.to(device=dev, dtype=grads.dtype).contiguous()
         if g.numel() not in (1, grads.size(0)):
             raise ValueError("grad_output must have 1 or batch elements")
-        d = _lib.Desc()
-        d.batch, d.max_frames, d.alphabet, d.max_targets = grads.size(0), grads.size(1), grads.size(2), 0
-        d.blank_idx, d.dtype = 0, _DTYPES[grads.dtype]
-        d.targets_itype = d.lengths_itype = _lib.E2E_I64
-        d.grads_stride_b, d.grads_stride_t = grads.stride(0), grads.stride(1)
-        d.logits_stride_b, d.logits_stride_t = grads.stride(0), grads.stride(1)
+        key = (grads.shape, grads.stride(), grads.dtype)
+        d = self._scale_desc.get(key)
+        if d is None:
+            d = _lib.Desc()
+            d.batch, d.max_frames, d.alphabet, d.max_targets = grads.size(0), grads.size(1), grads.size(2), 0
+            d.blank_idx, d.dtype = 0, _DTYPES[grads.dtype]
+            d.targets_itype = d.lengths_itype = _lib.E2E_I64
+            d.grads_stride_b, d.grads_stride_t = grads.stride(0), grads.stride(1)
+            d.logits_stride_b, d.logits_stride_t = grads.stride(0), grads.stride(1)
+            if len(self._scale_desc) > 256:
+                self._scale_desc.clear()
+            self._scale_desc[key] = d
         with _on_device(dev):
             _lib.check(self._L.e2e_ctc_scale_rows_device(ctypes.byref(d), _ptr(grads), _ptr(g), g.numel(), _stream(dev)))
         return grads
