@@ -165,9 +165,11 @@ static bool make_sweep_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
 // Wave kernel (fused small-alphabet path): variants by (cells per lane, lattice warps per sweep).
 static bool make_wave_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   if (!fused || d.dtype == E2E_F64 || d.alphabet > kDenseMaxAlphabet) return false;
-  // E2E_CTC_WAVE: 0 never, 1 whenever a variant fits (testing), unset: latency shapes only -- every
-  // utterance's two CTAs resident at once (2B <= 148 SMs) and at most four lattice warps per sweep; larger
-  // batches are throughput-bound and run the one-warp-per-sweep kernel.
+  // E2E_CTC_WAVE: 0 never, 1 whenever a variant fits (testing), unset: latency shapes only -- at most two
+  // rounds of resident clusters (one 2-CTA cluster per utterance, one CTA per SM: B <= 148) and two to four
+  // lattice warps per sweep; measured on c2-shaped batches the wave kernel wins up to B = 148 (0.215 vs
+  // 0.338 ms) and ties at B = 256; larger batches and short lattices (one lattice warp: OCR-sized targets,
+  // where many utterances share an SM) are throughput-bound and run the one-warp-per-sweep kernel.
   const int mode = env_int("E2E_CTC_WAVE", -1);
   if (mode == 0 || env_int("E2E_CTC_NO_FUSED", 0) || env_int("E2E_CTC_LEGACY", 0) ||
       env_int("E2E_CTC_CELLS_PER_LANE", 0) || env_int("E2E_CTC_LATTICE_WARPS", 0)) return false;
@@ -177,7 +179,7 @@ static bool make_wave_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   int K = 0, NW = 0;
   for (const auto& v : kVar)
     if (32 * v[0] * v[1] >= S && (!fw || v[1] == fw) && (!fk || v[0] == fk) && !K) { K = v[0]; NW = v[1]; }
-  if (mode != 1 && (2 * d.batch > 148 || NW > 4)) return false;
+  if (mode != 1 && (d.batch > 148 || NW > 4 || (NW == 1 && 2 * d.batch > 148))) return false;
   if (!K) return false;
   WaveLayout L;
   L.K = K; L.NW = NW;
