@@ -590,3 +590,35 @@ def test_host_engine_traffic_and_pinned_buffers(e2e):
     ref_leaf = x.clone().requires_grad_()
     oracle.ctc_loss_module(oracle.engine(0), ref_leaf, tg, ll, tl, reduce=True, size_average=True).backward()
     assert_parity(leaf.grad, ref_leaf.grad, what="host module grad")
+
+
+@pytest.mark.parametrize("chunks", [2, 3, 8])
+def test_host_engine_chunked_pipeline(e2e, chunks):
+    """The host entry point cuts a batch-major batch into chunks of utterances that flow through copy-in /
+    kernels / copy-out on separate streams: same results as the single-stream path, ragged last chunk,
+    infeasible rows, bf16; time-major host tensors take the single-stream path; bad lengths are rejected
+    on the host before anything is enqueued."""
+    x, tg, ll, tl = oracle.make_inputs(7, 60, 11, 3, 12, 77)
+    ll[2] = 5                                                         # infeasible: T < L
+    tl[2] = 9
+    eng = e2e.CTCLossEngine(0)
+    l_one, g_one = _with_env({"E2E_CTC_HOST_CHUNKS": "1"}, lambda: eng.compute(x, tg, ll, tl, from_logits=True))
+    l_ch, g_ch = _with_env({"E2E_CTC_HOST_CHUNKS": str(chunks)}, lambda: eng.compute(x, tg, ll, tl, from_logits=True))
+    assert not l_ch.is_cuda and torch.isinf(l_ch[2]) and torch.isnan(g_ch[2]).all()
+    assert torch.equal(torch.nan_to_num(l_one, 0, 0, 0), torch.nan_to_num(l_ch, 0, 0, 0))
+    assert torch.equal(torch.isnan(g_one), torch.isnan(g_ch))
+    assert_parity(g_ch, g_one, what="chunked vs single-stream grads")
+    l_ref, g_ref = oracle.engine(0).compute(torch.log_softmax(x, 2), tg, ll, tl)
+    assert_parity(l_ch, l_ref, what="chunked host losses")
+    xb = x.to(torch.bfloat16)
+    lb1, gb1 = _with_env({"E2E_CTC_HOST_CHUNKS": "1"}, lambda: eng.compute(xb, tg, ll, tl, from_logits=True))
+    lbc, gbc = _with_env({"E2E_CTC_HOST_CHUNKS": str(chunks)}, lambda: eng.compute(xb, tg, ll, tl, from_logits=True))
+    assert torch.equal(torch.nan_to_num(gb1.float(), 0, 0, 0), torch.nan_to_num(gbc.float(), 0, 0, 0))
+    x_tm = x.permute(1, 0, 2).contiguous().permute(1, 0, 2)           # time-major storage, batch-major view
+    l_tm, g_tm = _with_env({"E2E_CTC_HOST_CHUNKS": str(chunks)}, lambda: eng.compute(x_tm, tg, ll, tl, from_logits=True))
+    assert_parity(g_tm, g_one, what="time-major host grads")
+    with pytest.raises(ValueError):
+        _with_env({"E2E_CTC_HOST_CHUNKS": str(chunks)},
+                  lambda: eng.compute(x, tg, torch.tensor([60, 61, 60, 60, 60, 60, 60]), tl, from_logits=True))
+    with pytest.raises(ValueError):
+        eng.compute(x, torch.full_like(tg, 11), ll, tl, from_logits=True)
