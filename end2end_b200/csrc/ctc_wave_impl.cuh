@@ -12,22 +12,30 @@
 //    indexes lattice cell m' = S-1-m.  Each sweep stores its first half of the frames to a global stash
 //    (L2), the two meet once through a global flag, and in its second half each multiplies its own cells
 //    with the other sweep's stashed row: the dependent chain is T frames, not 2T.
-//  * Warp roles inside a CTA, decoupled by shared-memory rings and monotonic progress counters:
-//      producers : fused row log-softmax.  One warp per frame: coalesced row load, warp-shuffle max /
-//                  sum-exp, emissions p(t,v) written as doubles into the E ring, chunks ahead of the sweep.
+//  * Warp roles inside a CTA, decoupled by shared-memory rings and monotonic progress words
+//    (st.release / ld.acquire at CTA scope, no block barrier anywhere in the frame loops):
+//      producers : fused row log-softmax, ONE LANE PER FRAME over blocks of 32 frames (no cross-lane
+//                  reductions); emissions p(t,v) land as doubles in the E ring, blocks ahead of the sweep.
 //      lattice   : NW warps, K cells per lane (cells alternate blank,label).  The s-1/s-2 transitions
 //                  cross lanes with one 64-bit shuffle; they cross WARPS through a 16-byte self-validating
 //                  shared-memory slot per frame (value + exponent + sequence tag in one vector store), so
-//                  warp w simply runs a frame or more behind warp w-1: a software wavefront with no
-//                  barrier on the recurrence.  Each frame the lanes drop the top 32 bits of their cells
-//                  (+ the lane's block exponent) into the `val` ring and do nothing else.
+//                  warp w runs one 4-frame group behind warp w-1: a software wavefront.  Frames are swept
+//                  in fully unrolled groups of four with the group's emissions and boundary slots fetched
+//                  up front; each frame the lanes drop the top 32 bits of their cells (+ the lane's block
+//                  exponent) into the `val` ring and do nothing else.
 //      combiners : drain the val ring, frames round-robin.  First half: copy rows to the global stash.
 //                  Second half: cp.async-prefetch the other sweep's stashed row, multiply, normalise by
-//                  Z = sum_s alpha*beta, sum the posteriors per symbol with integer shared-memory atomics
-//                  (bitwise reproducible) and write the gradient row scale * (softmax - posterior).
+//                  Z = sum_s alpha*beta, write each label cell's posterior into a row GROUPED BY SYMBOL
+//                  (counting sort of the labels, built once) and sum every symbol's contiguous slice in a
+//                  fixed order -- no atomics, bitwise reproducible -- into the gradient row
+//                  scale * (softmax - posterior).
 //  * Arithmetic: LINEAR-domain fp64 with a per-lane block exponent (value = x * 2^e).  A cell update is
-//    DADD (+ predicated DADD) + DMUL; the block exponents are re-centred every second frame from a
-//    snapshot of the previous frame, folded into the emission multipliers (ctc_sweep_impl.cuh scheme).
+//    DADD (+ DFMA for the repeat-label skip) + DMUL; the block exponents are re-centred once per 4-frame
+//    group from a snapshot two frames earlier, folded into the emission multipliers; a massless lane takes
+//    the exponent of the nearest lane with mass below it (ballot + indexed shuffle).
+//  * The kernel image must stay small: with three roles resident on every SM the instruction cache is a
+//    first-order constraint, hence runtime `BWD` outside the lattice loop and rolled loops in
+//    the producer / prologue paths.
 #pragma once
 #include <cstdlib>
 #include <type_traits>
