@@ -23,6 +23,7 @@ EXPORTS = (
     "e2e_ctc_engine_create", "e2e_ctc_engine_destroy", "e2e_ctc_engine_loss_host",
     "e2e_ctc_engine_greedy_host", "e2e_ctc_engine_last_traffic", "e2e_ctc_launch_count",
     "e2e_ctc_profile_enable", "e2e_ctc_profile_read",
+    "e2e_ctc_comm_unique_id", "e2e_ctc_comm_create", "e2e_ctc_comm_destroy", "e2e_ctc_comm_allreduce_sum",
 )
 KERNEL_KINDS = ("row_stats", "lattice", "gradient", "loss_reduce", "argmax", "collapse", "scale_rows")
 
@@ -91,6 +92,13 @@ def load():
     L.e2e_ctc_launch_count.restype = ctypes.c_uint64
     L.e2e_ctc_profile_enable.argtypes = [i32]
     L.e2e_ctc_profile_read.argtypes = [ctypes.POINTER(dbl), ctypes.POINTER(ctypes.c_uint64), i32]
+    L.e2e_ctc_comm_unique_id.argtypes = [vp]
+    L.e2e_ctc_comm_create.argtypes = [vp, i32, i32, ctypes.POINTER(vp)]
+    L.e2e_ctc_comm_destroy.argtypes = [vp]
+    L.e2e_ctc_comm_destroy.restype = None
+    L.e2e_ctc_comm_allreduce_sum.argtypes = [vp, vp, ctypes.c_int64, i32, vp]
+    for name in ("e2e_ctc_comm_unique_id", "e2e_ctc_comm_create", "e2e_ctc_comm_allreduce_sum"):
+        getattr(L, name).restype = ctypes.c_int
     for name in ("e2e_ctc_get_limits", "e2e_ctc_loss_forward_device", "e2e_ctc_loss_backward_device",
                  "e2e_ctc_loss_fwd_bwd_device", "e2e_ctc_loss_step_device", "e2e_ctc_scale_rows_device", "e2e_ctc_loss_reduce_device", "e2e_ctc_loss_check_device",
                  "e2e_ctc_greedy_decode_device", "e2e_ctc_engine_create", "e2e_ctc_engine_loss_host",

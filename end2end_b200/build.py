@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libe2e_ctc.so")
-SOURCES = ["api.cu", "ctc_rowstats.cu", "ctc_lattice.cu", "ctc_lattice_nw1.cu", "ctc_lattice_nw2.cu", "ctc_lattice_nw4.cu",
+SOURCES = ["api.cu", "comm.cu", "ctc_rowstats.cu", "ctc_lattice.cu", "ctc_lattice_nw1.cu", "ctc_lattice_nw2.cu", "ctc_lattice_nw4.cu",
            "ctc_wave_a.cu", "ctc_wave_b.cu", "ctc_sweep_a.cu", "ctc_sweep_b.cu", "ctc_sweep_c.cu", "ctc_sweep_d.cu",
            "ctc_grad.cu", "ctc_greedy.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -63,7 +63,7 @@ def build(force=False, verbose=False, extra=()):
         list(ex.map(run, jobs))
     objs = [os.path.join(OBJDIR, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _stale(LIB, objs):
-        run([nvcc, *ARCH, "-shared", "-o", LIB, *objs])
+        run([nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-ldl"])
     return LIB
 
 

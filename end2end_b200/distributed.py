@@ -57,6 +57,57 @@ def take_shard(indices, logits, targets, logits_lengths, targets_lengths, time_m
             targets_lengths.index_select(0, idx.to(targets_lengths.device)))
 
 
+class LossComm:
+    """The library-owned NCCL communicator for the one exchange of this path (``e2e_ctc_comm_*`` in
+    include/e2e_ctc.h): an in-place all-reduce of the reduced loss scalar, enqueued on the caller's stream
+    by the same library that enqueued the kernels.  Built once per process over the default process group
+    (the 128-byte NCCL id travels through ``torch.distributed``); ``LossComm.get()`` returns ``None`` when
+    there is nothing to build it from (no process group, a non-NCCL backend, libnccl missing), and the
+    caller falls back to ``dist.all_reduce``."""
+    _instance, _tried = None, False
+
+    def __init__(self, handle, L):
+        self.handle, self._L = handle, L
+
+    @classmethod
+    def get(cls):
+        if cls._tried:
+            return cls._instance
+        cls._tried = True
+        import ctypes
+        import os
+        from . import _lib
+        if os.environ.get("E2E_CTC_NO_LIB_COMM") or not (dist.is_available() and dist.is_initialized()):
+            return None
+        if dist.get_backend() != "nccl" or dist.get_world_size() < 2 or not torch.cuda.is_available():
+            return None
+        L = _lib.load()
+        rank, world = dist.get_rank(), dist.get_world_size()
+        buf = ctypes.create_string_buffer(128)
+        ok = 1
+        if rank == 0 and L.e2e_ctc_comm_unique_id(buf) != 0:
+            ok = 0
+        box = [bytes(buf.raw) if ok else None]
+        dist.broadcast_object_list(box, src=0)          # every rank learns the id (or that rank 0 has no libnccl)
+        if box[0] is None:
+            return None
+        h = ctypes.c_void_p()
+        rc = L.e2e_ctc_comm_create(box[0], world, rank, ctypes.byref(h))
+        flag = torch.tensor([1 if rc == 0 else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)     # all ranks or none
+        if int(flag.item()) == 0:
+            return None
+        cls._instance = cls(h, L)
+        return cls._instance
+
+    def allreduce_sum_(self, t):
+        """In-place sum of the CUDA tensor ``t`` over the ranks, on the current stream."""
+        from . import _lib
+        from .engine import _DTYPES, _stream
+        _lib.check(self._L.e2e_ctc_comm_allreduce_sum(self.handle, t.data_ptr(), t.numel(), _DTYPES[t.dtype], _stream(t.device)))
+        return t
+
+
 class _ShardedLossFunction(Function):
     @staticmethod
     def forward(ctx, engine, logits, targets, logits_lengths, targets_lengths, from_logits, mean,
@@ -74,8 +125,12 @@ class _ShardedLossFunction(Function):
             # all-reduce buffer and the result -- no host-side arithmetic around the collective
             _, ctx.grads, total, _ = engine.step(logits, targets, logits_lengths, targets_lengths, from_logits,
                                                  grad_scale=ctx.folded, reduce_scale=ctx.folded)
-            if reducing:
-                dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)   # THE collective of this path
+            if reducing:                                                    # THE collective of this path
+                comm = LossComm.get() if group is None else None
+                if comm is not None:
+                    comm.allreduce_sum_(total)
+                else:
+                    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
             ctx.inv_n = ctx.folded if mean else None
             return total
         if logits.is_cuda and need_grad:

@@ -154,6 +154,22 @@ int e2e_ctc_loss_reduce_device(const void* losses, int32_t dtype, int32_t batch,
  * Synchronises `cuda_stream`. */
 int e2e_ctc_loss_check_device(const void* workspace, int32_t* status_host, void* cuda_stream);
 
+/* ------------------------------------------------------------- multi-GPU: the one exchange ---- */
+
+/* Utterances are independent (forward_backward.cpp:38-52), so a batch shards across GPUs with no
+ * data-path collective; the only exchange is ONE NCCL all-reduce of the reduced loss scalar
+ * (modules/ctc_loss.py:52-56 summed over ranks).  The communicator is owned by the library (libnccl is
+ * resolved at run time) so that a host language without its own collective layer can shard a batch:
+ *   rank 0: e2e_ctc_comm_unique_id(id) -> ship the 128 bytes to every rank by any means;
+ *   every rank (its CUDA device current): e2e_ctc_comm_create(id, nranks, rank, &comm)  [collective];
+ *   per step, after e2e_ctc_loss_step_device(..., reduced, ...):
+ *       e2e_ctc_comm_allreduce_sum(comm, reduced, 1, dtype, stream)                    [in place]. */
+typedef struct e2e_ctc_comm e2e_ctc_comm;
+int e2e_ctc_comm_unique_id(void* out_id128);
+int e2e_ctc_comm_create(const void* id128, int32_t nranks, int32_t rank, e2e_ctc_comm** out);
+void e2e_ctc_comm_destroy(e2e_ctc_comm* comm);
+int e2e_ctc_comm_allreduce_sum(e2e_ctc_comm* comm, void* buf, int64_t count, int32_t dtype, void* cuda_stream);
+
 /* --------------------------------------------------------------- greedy decode, device ----- */
 
 size_t e2e_ctc_greedy_workspace_bytes(const e2e_ctc_desc* desc);
