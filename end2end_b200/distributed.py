@@ -81,6 +81,12 @@ class LossComm:
             return None
         if dist.get_backend() != "nccl" or dist.get_world_size() < 2 or not torch.cuda.is_available():
             return None
+        # Measured anomaly (profiles/r01/scale_r01e.md): a 2-rank communicator created here on a box with MORE
+        # than two GPUs (2 of 8 on an NVSwitch node) runs the scalar all-reduce 2-3x slower than c10d's own
+        # communicator, while 2 of 2, 4 of 8 and 8 of 8 are faster than c10d.  Until that is understood the
+        # partial-box two-rank case stays on c10d (E2E_CTC_LIB_COMM=1 forces the library communicator).
+        if dist.get_world_size() == 2 and torch.cuda.device_count() > 2 and not os.environ.get("E2E_CTC_LIB_COMM"):
+            return None
         L = _lib.load()
         rank, world = dist.get_rank(), dist.get_world_size()
         buf = ctypes.create_string_buffer(128)
