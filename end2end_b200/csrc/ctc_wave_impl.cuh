@@ -335,7 +335,7 @@ __device__ void wave_lattice(const WaveParams& p, const WaveView& sv, int b, int
         if (!FULLG && has_in && i > 0) q = wv_ld_volatile_v4(slot);
         if (FULLG && has_in && i > 0) {
           src_e = (int)q.z;
-          const double bin = __hiloint2double((int)q.y, (int)q.x) * pow2i(src_e - e);
+          const double bin = __hiloint2double((int)q.y, (int)q.x) * pow2i(min(src_e - e, 1000));   // finite whatever the two scales are
           if (lane == 0) bxs = bin;
         }
         if (k == 2) {
@@ -343,14 +343,25 @@ __device__ void wave_lattice(const WaveParams& p, const WaveView& sv, int b, int
           int mhi = 0;
 #pragma unroll
           for (int j = 0; j < K; j++) mhi = max(mhi, __double2hiint(x[j]));
-          // a massless lane takes the new exponent of the nearest lane with mass below it (the side its mass will
-          // come from; below the first such lane of warps > 0: the exponent of the last boundary value), so that
-          // the mass front always runs into lanes whose scale is at most a few frames stale
-          const unsigned live = __ballot_sync(FULL, mhi != 0);
-          const unsigned below = live & ((1u << lane) - 1u);
-          const int own = e + ((mhi >> 20) - 1023);
-          const int from = __shfl_sync(FULL, own, below ? 31 - __clz(below) : 0);
-          const int en = mhi != 0 ? own : (below ? from : (has_in ? src_e : e));
+          // New exponent of the lane: its own block maximum, but for a lane WITH mass never more than kExpSlack
+          // below the new exponent of the lane its mass comes from (so incoming cells are scaled by at most
+          // 2^kExpSlack: no overflow when a large mass follows a tiny front trickle -- tight alignments under
+          // very peaky emissions); a lane WITHOUT mass takes the exponent of the nearest lane with mass below
+          // it exactly (below the first such lane of warps > 0: the last boundary exponent), so the front
+          // always runs into a scale that is at most a few frames stale.  Both rules are one prefix maximum:
+          //   en_i = max_{j <= i} (own_j + D_j) - D_i,   D_i = kExpSlack * #{lanes with mass <= i}.
+          constexpr int kExpSlack = 512;
+          const bool alive = mhi != 0;
+          const unsigned live = __ballot_sync(FULL, alive);
+          const int D = kExpSlack * __popc(live & ((2u << lane) - 1u));
+          int v = alive ? e + ((mhi >> 20) - 1023) + D : 2 * kNegExp;
+          if (has_in) v = max(v, src_e);              // the previous warp's boundary lane, as lane -1 (D = 0)
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(FULL, v, d);
+            if (lane >= d) v = max(v, t);
+          }
+          const int en = v < kNegExp ? e : v - D;     // nothing with mass up to here: keep the scale
           const int nb_en = __shfl_up_sync(FULL, en, 1);
           en_next = en;
           f_next = pow2i(e - en);
@@ -379,7 +390,7 @@ __device__ void wave_lattice(const WaveParams& p, const WaveView& sv, int b, int
           while ((int)q.w != i) q = wv_ld_volatile_v4(slot);
           WV_DBG_ADD(4, WV_CLK() - t0);
           src_e = (int)q.z;
-          const double bin = __hiloint2double((int)q.y, (int)q.x) * pow2i(src_e - e);
+          const double bin = __hiloint2double((int)q.y, (int)q.x) * pow2i(min(src_e - e, 1000));   // finite whatever the two scales are
           if (lane == 0) bxs = bin;
         }
         {

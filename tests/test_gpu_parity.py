@@ -304,6 +304,30 @@ def test_wave_kernel_is_the_default_for_latency_shapes(e2e):
     assert_parity(g_w, g_s, what="wave vs sweep grads")
 
 
+def test_wave_kernel_tight_peaky_alignments(e2e):
+    """T_i == L_i + repeats (exactly one alignment) under very peaky emissions (logits x10): the single
+    feasible path runs along the mass front, tens of orders of magnitude below the dead-end mass behind it.
+    Found by the differential fuzz (scratch/gpu_fuzz.py); the per-lane block exponents must keep it."""
+    g = torch.Generator().manual_seed(5)
+    B, V = 6, 5
+    tl = torch.tensor([55, 73, 66, 40, 120, 9])
+    T_ = 170
+    tg = torch.randint(1, V, (B, 120), generator=g)
+    ll = torch.zeros(B, dtype=torch.int64)
+    for b in range(B):
+        L = int(tl[b])
+        rep = int((tg[b, 1:L] == tg[b, :L - 1]).sum())
+        ll[b] = L + rep + (b % 3)                      # tight, or one/two spare frames
+    assert int(ll.max()) <= T_
+    x = torch.randn(B, T_, V, generator=g) * 10.0
+    lp = torch.log_softmax(x, 2)
+    l_ref, g_ref = oracle.engine(0).compute(lp, tg, ll, tl)
+    assert torch.isfinite(l_ref).all()
+    l_gpu, g_gpu = _with_env({"E2E_CTC_WAVE": "1"}, lambda: e2e.CTCLossEngine(0).compute(lp.cuda(), *cuda(tg, ll, tl)))
+    assert_parity(l_gpu, l_ref, what="tight peaky losses")
+    assert_parity(g_gpu, g_ref, what="tight peaky grads")
+
+
 @pytest.mark.parametrize("fused", [True, False])
 def test_two_lattice_warps_long_targets(e2e, fused):
     """2L+1 > 1280 cells: two lattice warps per sweep exchange their boundary cells through shared memory."""
