@@ -644,8 +644,14 @@ __device__ void run_combiner(const LatticeParams& p, const SmemView& sv, int b, 
 #pragma unroll
         for (int g = 0; g < NW; g++) tot += lsum[g] > 0.0 ? lsum[g] * pow2i(El[g] - emax) : 0.0;
         tot = warp_sum(tot);
-        invz = 1.0 / tot;   // tot == 0 (no path survives): NaN posteriors; the forward sweep flags the utterance
-        Ez = emax;
+        // 1/Z (times 2^31 in dense mode) as a mantissa in [1,2) with its power of two folded into the reference
+        // exponent, so that the per-lane scale stays finite for lanes that carry a stale exponent and no mass
+        // (0 * inf = NaN converted to a spurious posterior; see ctc_sweep_impl.cuh).  tot == 0 or NaN: garbage
+        // posteriors; the forward sweep flags the utterance and the block is overwritten with NaN.
+        const double rz = (p.dense ? 2147483648.0 : 1.0) / tot;
+        const int kz = ((__double2hiint(rz) >> 20) & 0x7ff) - 1023;
+        invz = __hiloint2double((__double2hiint(rz) & 0x800fffff) | 0x3ff00000, __double2loint(rz));
+        Ez = emax - kz;
         have_z = true;
       }
       uint32_t* arow = sv.acc + (size_t)fr * p.vpad;
@@ -657,7 +663,7 @@ __device__ void run_combiner(const LatticeParams& p, const SmemView& sv, int b, 
         for (int g = 0; g < NW; g++) {
           const uint32_t* ve = vrow + g * 32 * WORDS;
           const uint32_t* oe = orow + g * 32 * WORDS;
-          const double ccl = pow2i((int)ve[K] + (int)oe[K] - Ez) * invz * 2147483648.0;
+          const double ccl = pow2i((int)ve[K] + (int)oe[K] - Ez) * invz;
           const int* labp = sv.lab + (g * 32 + lane) * H;
           double bs = 0.0;
 #pragma unroll

@@ -442,15 +442,24 @@ __device__ void run_sweep(const SweepParams& p, unsigned char* smem, int b, int 
         for (int u = 0; u < H; u++) lsum += pr[u];
         const int emax = warp_max_int(lsum > 0.0 ? El : 4 * kNegExp);
         const double tot = warp_sum(lsum > 0.0 ? lsum * pow2i(El - emax) : 0.0);
-        invz = 1.0 / tot;   // tot == 0 (no path survives): NaN posteriors; the forward sweep flags the utterance
-        Ez = emax;
+        // 1/Z (times 2^31 in dense mode: fixed-point posteriors) as a mantissa in [1,2) with its power of two
+        // folded into the reference exponent: the per-lane scale 2^(El - Ez) * invz then stays FINITE whatever
+        // stale exponent a lane without mass carries (0 * finite = 0; an infinite scale made 0 * inf = NaN, and
+        // the float-to-integer conversion of NaN put a spurious posterior of 1 on such a lane's symbols --
+        // tight alignments under very peaky emissions, found by scratch/gpu_fuzz.py).
+        // tot == 0 or NaN (no path survives): garbage posteriors; the forward sweep flags the utterance and the
+        // block is overwritten with NaN.
+        const double rz = (p.dense ? 2147483648.0 : 1.0) / tot;
+        const int kz = ((__double2hiint(rz) >> 20) & 0x7ff) - 1023;
+        invz = __hiloint2double((__double2hiint(rz) & 0x800fffff) | 0x3ff00000, __double2loint(rz));
+        Ez = emax - kz;
         have_z = true;
       }
       if (p.dense) {
         // posteriors summed per symbol with integer shared-memory atomics (fixed point 2^-31: the sum per
         // symbol is <= 1; integer adds commute, so the gradient is bitwise reproducible)
         uint32_t* arow = acc + (size_t)(i & 1) * p.vpad;
-        const double ccl = pow2i(El - Ez) * invz * 2147483648.0;
+        const double ccl = pow2i(El - Ez) * invz;
 #pragma unroll
         for (int u = 0; u < H; u++) atomicAdd(arow + ecol[u], __double2uint_rn(pr[u] * ccl));   // cells past L_i add 0 to the spare slot V
         const uint32_t qb = __reduce_add_sync(FULL, __double2uint_rn(bs * ccl));
