@@ -245,7 +245,11 @@ __device__ __forceinline__ void snapshot(SweepState<K, ET>& s, int lane) {
   int bec = BWD ? __shfl_down_sync(FULL, ec, 1) : __shfl_up_sync(FULL, ec, 1);
   const bool edge = BWD ? (lane == 31) : (lane == 0);
   if (edge) bec = kNegExp;
-  const int en = max(ec, bec);
+  // Own exponent, but at most kExpSlack below the exponent of the lane the mass comes from, so that incoming
+  // cells are scaled by at most 2^kExpSlack.  (A plain max(ec, bec) flushed a lane whose own mass is more than
+  // 2^1022 below its neighbour's -- the only feasible path of a tight alignment under very peaky emissions.)
+  constexpr int kExpSlack = 900;
+  const int en = max(ec, bec - kExpSlack);
   const int ben = BWD ? __shfl_down_sync(FULL, en, 1) : __shfl_up_sync(FULL, en, 1);
   s.en_next = en;
   s.f_next = pow2i(s.e - en);

@@ -646,3 +646,43 @@ def test_host_engine_chunked_pipeline(e2e, chunks):
                   lambda: eng.compute(x, tg, torch.tensor([60, 61, 60, 60, 60, 60, 60]), tl, from_logits=True))
     with pytest.raises(ValueError):
         eng.compute(x, torch.full_like(tg, 11), ll, tl, from_logits=True)
+
+
+def test_differential_fuzz_wave_vs_sweep(e2e):
+    """Two independent lattice implementations (the wave kernel, forced, and the one-warp-per-sweep kernel) on
+    random shapes, dtypes, strides, blanks and emission scales: losses, gradients and NaN / inf positions must
+    agree.  (The longer scratch/gpu_fuzz.py run found the 0*inf posterior bug fixed in DESIGN.md 8b.)"""
+    import random
+    rng = random.Random(20261017)
+    for it in range(60):
+        B = rng.choice([1, 2, 3, 5, 8, 17])
+        T_ = rng.choice([1, 2, 3, 7, 8, 9, 31, 32, 33, 64, 100, 129, 257])
+        V = rng.choice([3, 5, 29, 32, 33, 64, 96, 128])   # V = 2 (one label: every target a repeat): DESIGN.md 8b
+        Lmax = rng.choice([0, 1, 2, 5, 31, 32, 63, 64, 65, 127, 128, 200, 255])
+        dt = rng.choice([torch.float32, torch.float32, torch.bfloat16, torch.float16])
+        from_logits = rng.random() < 0.5
+        time_major = rng.random() < 0.3
+        blank = rng.randrange(V)
+        scale = rng.choice([1.0, 1.0, 4.0, 10.0])
+        g = torch.Generator().manual_seed(rng.randrange(1 << 30))
+        x = torch.randn(B, T_, V, generator=g) * scale
+        if not from_logits:
+            x = torch.log_softmax(x, 2)
+        x = x.to(dt)
+        tl = torch.randint(0, Lmax + 1, (B,), generator=g)
+        tg = torch.randint(0, V, (B, max(Lmax, 1)), generator=g)[:, :Lmax]
+        tg = torch.where(tg == blank, (tg + 1) % V, tg)
+        ll = torch.randint(1, T_ + 1, (B,), generator=g)
+        if rng.random() < 0.5:
+            ll = torch.maximum(ll, torch.minimum(tl * 2, torch.tensor(T_)))
+        xc = x.cuda()
+        if time_major:
+            xc = xc.permute(1, 0, 2).contiguous().permute(1, 0, 2)
+        args = (xc, *cuda(tg, ll, tl))
+        l1, g1 = _with_env({"E2E_CTC_WAVE": "1"}, lambda: e2e.CTCLossEngine(blank).compute(*args, from_logits=from_logits))
+        l0, g0 = _with_env({"E2E_CTC_WAVE": "0"}, lambda: e2e.CTCLossEngine(blank).compute(*args, from_logits=from_logits))
+        tol = 2e-5 if dt == torch.float32 else (2.0 ** -7 if dt == torch.bfloat16 else 2.0 ** -10)
+        what = "fuzz case %d (B=%d T=%d V=%d Lmax=%d %s from_logits=%s tm=%s blank=%d x%g)" % (
+            it, B, T_, V, Lmax, dt, from_logits, time_major, blank, scale)
+        assert_parity(l1.float(), l0.float(), rtol=tol, atol=tol, what=what + " losses")
+        assert_parity(g1.float(), g0.float(), rtol=tol, atol=tol, what=what + " grads")
