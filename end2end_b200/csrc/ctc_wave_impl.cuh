@@ -335,7 +335,7 @@ __device__ void wave_lattice(const WaveParams& p, const WaveView& sv, int b, int
         if (!FULLG && has_in && i > 0) q = wv_ld_volatile_v4(slot);
         if (FULLG && has_in && i > 0) {
           src_e = (int)q.z;
-          const double bin = __hiloint2double((int)q.y, (int)q.x) * pow2i(min(src_e - e, 1000));   // finite whatever the two scales are
+          const double bin = __hiloint2double((int)q.y, (int)q.x) * pow2i(min(src_e - e, 600));   // bounded: a few more lane hops (2^192 each) before the next re-centring cannot overflow
           if (lane == 0) bxs = bin;
         }
         if (k == 2) {
@@ -350,7 +350,7 @@ __device__ void wave_lattice(const WaveParams& p, const WaveView& sv, int b, int
           // it exactly (below the first such lane of warps > 0: the last boundary exponent), so the front
           // always runs into a scale that is at most a few frames stale.  Both rules are one prefix maximum:
           //   en_i = max_{j <= i} (own_j + D_j) - D_i,   D_i = kExpSlack * #{lanes with mass <= i}.
-          constexpr int kExpSlack = 512;
+          constexpr int kExpSlack = 192;
           const bool alive = mhi != 0;
           const unsigned live = __ballot_sync(FULL, alive);
           const int D = kExpSlack * __popc(live & ((2u << lane) - 1u));
@@ -390,7 +390,7 @@ __device__ void wave_lattice(const WaveParams& p, const WaveView& sv, int b, int
           while ((int)q.w != i) q = wv_ld_volatile_v4(slot);
           WV_DBG_ADD(4, WV_CLK() - t0);
           src_e = (int)q.z;
-          const double bin = __hiloint2double((int)q.y, (int)q.x) * pow2i(min(src_e - e, 1000));   // finite whatever the two scales are
+          const double bin = __hiloint2double((int)q.y, (int)q.x) * pow2i(min(src_e - e, 600));   // bounded: a few more lane hops (2^192 each) before the next re-centring cannot overflow
           if (lane == 0) bxs = bin;
         }
         {
