@@ -177,6 +177,11 @@ def run_ours(args, wl):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
+        # The only collective of this path is a scalar all-reduce: NVLink SHARP multicast buys nothing, and its
+        # set-up makes a TWO-rank communicator on a larger NVSwitch box 2-3x slower per step (measured:
+        # profiles/r01/scale_r01e.md).  NCCL caches the setting at the first communicator, so it is set here.
+        if world == 2:      # with 4 or 8 ranks the in-switch reduction helps (8 ranks: 0.167 vs 0.219 ms/step)
+            os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
         dist.init_process_group("nccl", device_id=dev)
     from end2end_b200 import CTCLoss, CTCLossEngine, _lib
     from end2end_b200.distributed import ShardedCTCLoss

@@ -84,8 +84,11 @@ class LossComm:
         # Measured anomaly (profiles/r01/scale_r01e.md): a 2-rank communicator created here on a box with MORE
         # than two GPUs (2 of 8 on an NVSwitch node) runs the scalar all-reduce 2-3x slower than c10d's own
         # communicator, while 2 of 2, 4 of 8 and 8 of 8 are faster than c10d.  Until that is understood the
-        # partial-box two-rank case stays on c10d (E2E_CTC_LIB_COMM=1 forces the library communicator).
-        if dist.get_world_size() == 2 and torch.cuda.device_count() > 2 and not os.environ.get("E2E_CTC_LIB_COMM"):
+        # partial-box two-rank case stays on c10d (E2E_CTC_LIB_COMM=1 forces the library communicator).  Cause found:
+        # NVLS (NVLink SHARP multicast) set-up; with NCCL_NVLS_ENABLE=0 in the environment BEFORE the first NCCL
+        # communicator of the process the two-rank library communicator is the fastest option again (0.160 ms/step).
+        if (dist.get_world_size() == 2 and torch.cuda.device_count() > 2 and os.environ.get("NCCL_NVLS_ENABLE") != "0"
+                and not os.environ.get("E2E_CTC_LIB_COMM")):
             return None
         L = _lib.load()
         rank, world = dist.get_rank(), dist.get_world_size()
