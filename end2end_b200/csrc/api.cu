@@ -66,7 +66,7 @@ static int env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
-constexpr int kMaxTargets = (2 * 32 * kMaxCellsPerLane - 1) / 2;  // 2 warps x 40 cells per lane = 2560 cells -> L <= 1279
+constexpr int kMaxTargets = 639;      // 32 lanes x 10 blocks x 4 cells = 1280 >= 2L+1
 constexpr int kMaxAlphabet = 32768;
 
 static int check_desc(const e2e_ctc_desc* d, bool need_targets) {
@@ -99,218 +99,102 @@ static int check_desc(const e2e_ctc_desc* d, bool need_targets) {
   return E2E_OK;
 }
 
-// One-warp-per-sweep kernel: variants by cells per lane; f64 inputs use a subset (compile time).
-static const int kSweepK[] = {2, 4, 6, 8, 10, 12, 14, 16, 20, 24, 28, 32, 36, 40};
-static const int kSweepK64[] = {2, 4, 8, 16, 24, 40};
-
-static bool make_sweep_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
-  const int S = 2 * d.max_targets + 1;
-  const bool f64 = d.dtype == E2E_F64;
-  int K = 0;
-  if (f64) { for (int k : kSweepK64) if (32 * k >= S) { K = k; break; } }
-  else { for (int k : kSweepK) if (32 * k >= S) { K = k; break; } }
-  if (!K) return false;
-  p->sweep = 1;
-  p->K = K; p->NW = 1; p->cells = 32 * K; p->lanes = 32;
-  p->words = (K + 1 + 3) & ~3;
-  p->dense = fused && d.alphabet <= kDenseMaxAlphabet && env_int("E2E_CTC_NO_FUSED", 0) == 0;
-  p->rowlen = p->dense ? d.alphabet : d.max_targets + 1;
-  p->lstride = 0; p->np = 0; p->nc = 0; p->pfd = 0; p->chunk_log2 = 0;
-  p->post_stride = p->cells / 2 + 4;
-  p->vpad = p->dense ? ((d.alphabet + 1 + 3) & ~3) : 0;
-  const int H = K / 2, PF = K >= 24 ? 2 : 8;
-  const int et = f64 ? 8 : 4;
-  const int esz = f64 ? 8 : (d.dtype == E2E_F32 ? 4 : 2);
-  SweepLayout L;
-  L.vpad = p->vpad;
-  L.es = p->dense ? ((d.alphabet + 1) | 1) : (1 + 32 * H);
-  if (f64) L.rawrow = p->rowlen * 8;
-  else if (p->dense) L.rawrow = ((((d.alphabet * esz + 2 + 3) >> 2)) | 1) * 4;
-  else L.rawrow = ((d.max_targets + 1) | 1) * 4;
-  auto layout = [&](int cf) {
-    L.cf = cf;
-    size_t off = 0;
-    L.off_lab = 0; off = (size_t)align16i((size_t)(32 * H + 1) * 4);
-    L.off_warp = (int)off;
-    size_t w = 0;
-    L.w_E = (int)w; w = (size_t)align16i(w + (size_t)cf * L.es * et);
-    L.w_raw = (int)w; w = (size_t)align16i(w + (size_t)cf * L.rawrow);
-    L.w_stat = (int)w; w += (size_t)cf * 16;
-    L.w_rs = (int)w; w = (size_t)align16i(w + (size_t)cf * 4);
-    L.w_acc = (int)w; w += (size_t)2 * L.vpad * 4;
-    L.w_stage = (int)w; w += (size_t)PF * 32 * p->words * 4;
-    L.warp_bytes = (int)w;
-    return off + 2 * w;
-  };
-  int cf = env_int("E2E_CTC_CHUNK_FRAMES", 32);
-  if (cf != 8 && cf != 16 && cf != 32) cf = 32;
-  // several CTAs per SM when the batch is large; otherwise whatever fits
-  const size_t want = d.batch > 148 ? 56 * 1024 : 200 * 1024;
-  while (cf > 8 && layout(cf) > want) cf >>= 1;
-  const size_t smem = layout(cf);
-  if (smem > 220 * 1024) return false;
-  p->sw = L;
-  p->smem = smem;
-  const size_t rows = (size_t)d.batch * d.max_frames;
-  size_t off = 0;
-  p->off_status = off; off += 256;
-  p->off_flags = off; off += align256((size_t)d.batch * 4);
-  p->off_stats = off; off += p->dense ? 0 : align256(rows * (f64 ? 16 : 8));
-  p->off_stash = off; off += align256(rows * 32 * p->words * 4);
-  p->off_post = off; off += p->dense ? 0 : align256(rows * p->post_stride * 4);
-  p->total = off;
-  return true;
+// Tuning overrides for the lattice kernel's role counts and ring sizes, read ONCE per process (experiments
+// run one configuration per process; a production process never sets them).
+struct FzTune { int nc, np, nwarps, rv, r, pf, nap, cf, latency; };
+static const FzTune& fz_tune() {
+  static const FzTune t = {env_int("E2E_CTC_NC", 0), env_int("E2E_CTC_NP", 0), env_int("E2E_CTC_NWARPS", 0),
+                           env_int("E2E_CTC_RV", 0), env_int("E2E_CTC_R", 0), env_int("E2E_CTC_PF", 0),
+                           env_int("E2E_CTC_NAP", -1), env_int("E2E_CTC_CF", 0), env_int("E2E_CTC_LATENCY", -1)};
+  return t;
 }
 
-// Wave kernel (fused small-alphabet path): variants by (cells per lane, lattice warps per sweep).
-static bool make_wave_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
-  if (!fused || d.dtype == E2E_F64 || d.alphabet > kDenseMaxAlphabet) return false;
-  // E2E_CTC_WAVE: 0 never, 1 whenever a variant fits (testing), unset: latency shapes only -- at most two
-  // rounds of resident clusters (one 2-CTA cluster per utterance, one CTA per SM: B <= 148) and two to four
-  // lattice warps per sweep; measured on c2-shaped batches the wave kernel wins up to B = 148 (0.215 vs
-  // 0.338 ms) and ties at B = 256; larger batches and short lattices (one lattice warp: OCR-sized targets,
-  // where many utterances share an SM) are throughput-bound and run the one-warp-per-sweep kernel.
-  const int mode = env_int("E2E_CTC_WAVE", -1);
-  if (mode == 0 || env_int("E2E_CTC_NO_FUSED", 0) || env_int("E2E_CTC_LEGACY", 0) ||
-      env_int("E2E_CTC_CELLS_PER_LANE", 0) || env_int("E2E_CTC_LATTICE_WARPS", 0)) return false;
-  static const int kVar[][2] = {{4, 1}, {4, 2}, {4, 4}, {4, 8}, {8, 8}};
-  const int S = 2 * d.max_targets + 1;
-  const int fw = env_int("E2E_CTC_WAVE_NW", 0), fk = env_int("E2E_CTC_WAVE_K", 0);
-  int K = 0, NW = 0;
-  for (const auto& v : kVar)
-    if (32 * v[0] * v[1] >= S && (!fw || v[1] == fw) && (!fk || v[0] == fk) && !K) { K = v[0]; NW = v[1]; }
-  if (mode != 1 && (d.batch > 148 || NW > 4 || (NW == 1 && 2 * d.batch > 148))) return false;
-  if (!K) return false;
-  WaveLayout L;
-  L.K = K; L.NW = NW;
-  L.NC = env_int("E2E_CTC_WAVE_NC", NW >= 4 ? 6 : 2);
-  L.NP = env_int("E2E_CTC_WAVE_NP", NW >= 4 ? 2 : 1);
-  if (L.NC < 1 || L.NC > 8 || (L.NP != 1 && L.NP != 2 && L.NP != 4)) return false;
-  L.nap = env_int("E2E_CTC_WAVE_NAP", 32);
-  L.by_smsp = env_int("E2E_CTC_WAVE_BY_SMSP", 0);
-  if (L.by_smsp) {
-    int r = NW > L.NP ? NW : L.NP;
-    if ((L.NC + 1) / 2 > r) r = (L.NC + 1) / 2;
-    L.nwarps = 4 * r;
-  } else {
-    L.nwarps = NW + L.NC + L.NP;
-  }
-  if (L.nwarps > (NW <= 4 ? 16 : 32)) return false;
-  const int lanes = 32 * NW, roww = lanes * (K + 1);
-  L.es = (d.alphabet + 2) | 1;   // odd: the producer's lane-per-frame stores are bank-conflict free
-  L.vpad = (d.alphabet + 3) & ~3;
-  L.RV = env_int("E2E_CTC_WAVE_RV", lanes * K >= 1024 ? 16 : 32);
-  L.R = env_int("E2E_CTC_WAVE_R", 128);   // producer blocks are 32 frames: two per producer in flight
-  if (L.R < 64 || (L.R & (L.R - 1))) return false;
-  while (L.R > 64 && (size_t)L.R * L.es * 8 > (size_t)(NW >= 4 ? 64 : 40) * 1024) L.R >>= 1;
-  if (L.RV > L.R / 2) L.RV = L.R / 2;
-  if (L.RV < kWaveCF || (L.RV & (L.RV - 1))) return false;
+bool make_loss_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
+  const int Lmax = d.max_targets, V = d.alphabet;
+  const int NB = Lmax <= 63 ? 1 : (Lmax <= 127 ? 2 : (Lmax <= 255 ? 4 : (Lmax <= kMaxTargets ? 10 : 0)));
+  if (!NB) return false;
+  const FzTune& tn = fz_tune();
+  const bool dense = fused && V <= kDenseMaxAlphabet;
+  // latency shapes: every CTA of the launch has an SM to itself (one 2-CTA cluster per utterance), so the
+  // CTA is laid out for the shortest per-frame chain; otherwise several CTAs share an SM and the layout is
+  // sized for occupancy
+  bool latency = 2 * d.batch <= 148;
+  if (tn.latency == 0 || tn.latency == 1) latency = tn.latency == 1;
+  FzLayout L;
+  memset(&L, 0, sizeof(L));
+  L.NB = NB;
+  L.gather = dense ? 0 : 1;
+  const bool heavy_rows = !dense || V > 32;   // producer work per frame: a whole row of > 32 symbols, or a gather
+  const int maxw = NB <= 4 ? 8 : 5;
+  if (NB == 10) { L.NP = 1; L.NC = 3; L.nwarps = 5; }
+  else if (latency) { L.NP = heavy_rows ? 2 : 1; L.NC = heavy_rows ? 4 : 5; L.nwarps = 8; }
+  else { L.NP = heavy_rows ? 2 : 1; L.NC = NB >= 4 ? 3 : 2; L.nwarps = 1 + L.NP + L.NC; }
+  if (tn.np == 1 || tn.np == 2 || tn.np == 4) L.NP = tn.np;   // a power of two (the lattice masks with NP-1)
+  if (tn.nc >= 1 && tn.nc <= 8) L.NC = tn.nc;
+  if (tn.nwarps) L.nwarps = tn.nwarps;
+  if (L.nwarps < 1 + L.NP + L.NC) L.nwarps = 1 + L.NP + L.NC;
+  if (L.nwarps > maxw) return false;
+  L.PF = (latency && NB < 10) ? 4 : 2;
+  if (tn.pf == 2 || tn.pf == 4) L.PF = tn.pf;
+  L.CF = NB == 10 ? 4 : 8;
+  if (tn.cf == 4 || tn.cf == 8) L.CF = tn.cf;
+  L.RV = NB == 10 ? 8 : 16;
+  if (tn.rv >= 8 && !(tn.rv & (tn.rv - 1))) L.RV = tn.rv;
+  if (L.RV < 2 * L.CF) L.RV = 2 * L.CF;
+  L.nap = tn.nap >= 0 ? tn.nap : 32;
+  L.es = dense ? ((V + 2) | 1) : (64 * NB + 1);   // odd: the producers' lane-per-frame stores are bank-conflict free
+  L.PB = dense ? 32 : 8;
+  L.pb_log2 = dense ? 5 : 3;
+  L.R = 2 * L.PB;                                 // two producer blocks in flight
+  while (L.R < 128 && (size_t)2 * L.R * L.es * 8 <= (size_t)(latency ? 48 : 24) * 1024) L.R *= 2;
+  if (tn.r >= 2 * L.PB && !(tn.r & (tn.r - 1))) L.R = tn.r;
+  if (L.R > 16 * L.PB) L.R = 16 * L.PB;   // at most 16 emission blocks (one mbarrier each)
+  if (L.RV > 32) L.RV = 32;
+  auto ilog2 = [](int v) { int k = 0; while ((1 << k) < v) k++; return k; };
+  L.rv_log2 = ilog2(L.RV);
+  L.neb_log2 = ilog2(L.R / L.PB);
+  L.neb_mask = L.R / L.PB - 1;
+  const int nbp = (NB + 3) & ~3;
+  L.vframe = NB * 640 + 32 * nbp * 4;
+  L.srow = 640 * NB;
+  L.prow = 64 * NB + 4;
   size_t off = 0;
-  L.off_lab = 0; off = (size_t)align16i((size_t)(lanes * K / 2 + 1) * 4);
-  L.off_occ = (int)off; off = (size_t)align16i(off + (size_t)(lanes * K / 2 + d.alphabet + 2) * 4);   // label indices by symbol + offsets
+  L.off_lab = 0; off = (size_t)align16i((size_t)(64 * NB + 1) * 4);
+  L.off_occ = (int)off; off = (size_t)align16i(off + (size_t)(64 * NB + V + 2) * 4 * (dense ? 1 : 0));
   L.off_E = (int)off; off = (size_t)align16i(off + (size_t)L.R * L.es * 8);
-  L.off_valw = (int)off; off += (size_t)L.RV * lanes * K * 4;
-  L.off_vale = (int)off; off += (size_t)L.RV * lanes * 4;
-  L.off_stage = (int)off; off += (size_t)L.NC * kWavePF * (roww + 4) * 4;
-  L.off_acc = (int)off; off += (size_t)L.NC * (lanes * K / 2 + 4) * 4;   // one row of label posteriors per combiner warp (+ a spare slot)
-  L.off_bnd = (int)off; off += (size_t)NW * kWaveRB * 16;
-  L.off_ctl = (int)off; off += wave_ctl_bytes();
+  L.off_val = (int)off; off += (size_t)L.RV * L.vframe;
+  L.off_stage = (int)off; off += (size_t)L.NC * L.PF * L.srow;
+  L.off_post = (int)off; off = (size_t)align16i(off + (size_t)L.NC * L.prow * 4);
+  L.off_ctl = (int)off; off += fused_ctl_bytes();
   L.total = (int)off;
   if (off > 220 * 1024) return false;
-  p->wave = 1; p->sweep = 0; p->wv = L;
-  p->K = K; p->NW = NW; p->cells = lanes * K; p->lanes = lanes; p->words = K + 1;
-  p->dense = 1; p->rowlen = d.alphabet; p->vpad = L.vpad;
-  p->lstride = 0; p->np = L.NP; p->nc = L.NC; p->pfd = kWavePF; p->chunk_log2 = 3; p->post_stride = 0;
+  // roles: warp 0 sweeps the lattice; the helpers go to warps on the OTHER SM sub-partitions first (warp w
+  // runs on scheduler w % 4), combiners before producers
+  for (int w = 0; w < 16; w++) { L.role[w] = 3; L.ridx[w] = 0; }
+  L.role[0] = 0;
+  {
+    int order[16], n = 0;
+    for (int w = 1; w < L.nwarps; w++) if (w % 4 != 0) order[n++] = w;
+    for (int w = 1; w < L.nwarps; w++) if (w % 4 == 0) order[n++] = w;
+    int k = 0;
+    for (int q = 0; q < L.NC; q++) { L.role[order[k]] = 1; L.ridx[order[k]] = (signed char)q; k++; }
+    for (int q = 0; q < L.NP; q++) { L.role[order[k]] = 2; L.ridx[order[k]] = (signed char)q; k++; }
+  }
+  p->fz = L;
+  p->dense = dense ? 1 : 0;
+  p->cells = 128 * NB;
+  p->post_stride = p->cells / 2 + 4;
+  p->roww = 5 * 32 * NB;
   p->smem = off;
   const size_t rows = (size_t)d.batch * d.max_frames;
   size_t o = 0;
   p->off_status = o; o += 256;
   p->off_meet = o; o += align256((size_t)d.batch * 8);
   p->off_flags = o; o += align256((size_t)d.batch * 4);
-  p->off_stats = o;
-  p->off_stash = o; o += align256(rows * roww * 4);
-  p->off_post = o;
+  p->off_stats = o; o += dense ? 0 : align256(rows * (d.dtype == E2E_F64 ? 16 : 8));
+  p->off_stash = o; o += align256(rows * p->roww * 4);
+  p->off_post = o; o += dense ? 0 : align256(rows * p->post_stride * 4);
   p->total = o;
-  return true;
-}
-
-bool make_loss_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
-  p->wave = 0; p->off_meet = 0;
-  if (make_wave_plan(d, fused, p)) return true;
-  p->wave = 0;
-  p->sweep = 0;
-  if (env_int("E2E_CTC_LEGACY", 0) == 0 && make_sweep_plan(d, fused, p)) return true;
-  p->sweep = 0;
-  // (cells per lane, lattice warps) variants the lattice kernel is instantiated for, by capacity.
-  // A single warp issues at most ~0.5 instructions per cycle, so when the batch is too small to fill the
-  // SMs with independent utterances (latency mode) the lattice is spread over up to 4 warps with few
-  // cells per lane; with many utterances per SM (throughput mode) one warp per sweep avoids the
-  // per-frame named barrier and leaves the issue slots to other CTAs.
-  static const int kLatency[][2] = {{2, 1}, {2, 2}, {2, 4}, {4, 4}, {8, 4}, {16, 4}, {40, 2}};
-  static const int kThroughput[][2] = {{2, 1}, {4, 1}, {8, 1}, {16, 1}, {24, 1}, {40, 1}, {40, 2}};
-  const int S = 2 * d.max_targets + 1;
-  int mode = env_int("E2E_CTC_LATENCY_MODE", -1);
-  if (mode != 0 && mode != 1) mode = d.batch <= 148 ? 1 : 0;
-  const int (*tab)[2] = mode ? kLatency : kThroughput;
-  int K = 0, NW = 1;
-  const int fk = env_int("E2E_CTC_CELLS_PER_LANE", 0), fw = env_int("E2E_CTC_LATTICE_WARPS", 0);
-  if (fk || fw) {   // testing hook: force a variant if it exists and is large enough
-    static const int kAll[][2] = {{2, 1}, {4, 1}, {8, 1}, {16, 1}, {24, 1}, {40, 1}, {2, 2}, {40, 2}, {2, 4}, {4, 4}, {8, 4}, {16, 4}};
-    for (const auto& v : kAll)
-      if ((!fk || v[0] == fk) && (!fw || v[1] == fw) && 32 * v[0] * v[1] >= S && !K) { K = v[0]; NW = v[1]; }
-  }
-  if (!K) for (int i = 0; i < 7; i++) if (32 * tab[i][0] * tab[i][1] >= S) { K = tab[i][0]; NW = tab[i][1]; break; }
-  if (!K) return false;
-  p->K = K; p->NW = NW; p->cells = 32 * K * NW; p->lanes = 32 * NW;
-  p->words = (K + 1 + 3) & ~3;
-  // dense (fused) mode: whole rows staged by symbol; the kernel also does the log-softmax statistics and
-  // writes the gradient.  Otherwise emissions are gathered by label and K1 / K3 run around the lattice.
-  p->dense = fused && d.alphabet <= kDenseMaxAlphabet && env_int("E2E_CTC_NO_FUSED", 0) == 0;
-  p->rowlen = p->dense ? d.alphabet : d.max_targets + 1;
-  p->lstride = p->dense ? ((d.alphabet + 2 + 1) & ~1) : (2 + p->cells / 2);
-  p->post_stride = p->cells / 2 + 4;
-  p->vpad = p->dense ? ((d.alphabet + 3) & ~3) : 0;
-  p->np = (p->dense && mode) ? 4 : (p->rowlen <= 32 ? 1 : (p->rowlen <= 64 ? 2 : 4));
-  p->nc = (mode && K < 24) ? 4 : 2;   // the big-K variants are compiled for at most 2 combiner warps
-  p->pfd = 8 / p->nc;
-  const size_t rawsz = d.dtype == E2E_F64 ? 8 : 4;
-  auto layout = [&](int cs, LatticeSmem* L) {
-    const size_t ring = (size_t)kNumChunks << cs;
-    size_t off = 0;
-    L->lab = (int)off; off = align16i(off + (size_t)(p->cells / 2) * 4 + 4);      // labels, padded with blank to cells/2
-    L->misc = (int)off; off += 64 + 8 * 4 * kMaxProducerWarps;   // 4 ints, then the producers' log-sum-exp partials at +64
-    L->E = (int)off; off = align16i(off + ring * p->lstride * 8);
-    L->raw = (int)off; off = align16i(off + ring * p->rowlen * rawsz);
-    L->rstat = (int)off; off += ring * 16;
-    L->val = (int)off; off += ring * p->lanes * p->words * 4;
-    L->stage = (int)off; off += (size_t)p->nc * p->pfd * p->lanes * p->words * 4;
-    L->acc = (int)off; off = align16i(off + ring * p->vpad * 4);
-    L->bnd = (int)off; off += 16 * sizeof(Boundary);
-    L->red = (int)off; off += 256;
-    L->bars = (int)off; off += 128;
-    L->total = (int)off;
-    return off;
-  };
-  int cs = env_int("E2E_CTC_CHUNK_LOG2", -1);
-  if (cs < 0 || cs > 3) {  // aim at ~256 staged items per hand-off
-    cs = 3;
-    while (cs > 0 && (p->rowlen << cs) > 256) --cs;
-  }
-  LatticeSmem L;
-  // latency mode runs one CTA per SM anyway; throughput mode wants several CTAs resident per SM
-  while (cs > 0 && layout(cs, &L) > (size_t)(mode ? 160 : 72) * 1024) --cs;
-  if (layout(cs, &L) > 220 * 1024) return false;
-  p->chunk_log2 = cs;
-  p->sm = L;
-  p->smem = (size_t)L.total;
-  const size_t rows = (size_t)d.batch * d.max_frames;
-  size_t off = 0;
-  p->off_status = off; off += 256;
-  p->off_flags = off; off += align256((size_t)d.batch * 4);
-  p->off_stats = off; off += p->dense ? 0 : align256(rows * (d.dtype == E2E_F64 ? 16 : 8));
-  p->off_stash = off; off += align256(rows * p->lanes * p->words * 4);
-  p->off_post = off; off += p->dense ? 0 : align256(rows * p->post_stride * 4);
-  p->total = off;
   return true;
 }
 
@@ -323,11 +207,10 @@ static int check_ws(const void* ws, size_t have, size_t need) {
 // split path: K1 row statistics + lattice (gather mode; posteriors left in the workspace for K3)
 static int loss_forward(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
                         const void* in_len, const void* tgt_len, void* losses, char* ws, cudaStream_t s) {
-  E2E_CUDA_TRY(cudaMemsetAsync(ws + p.off_status, 0, 256, s));
+  E2E_CUDA_TRY(cudaMemsetAsync(ws + p.off_status, 0, p.off_flags, s));   // status word + the meet flags
   int rc = launch_row_stats(d, logits, ws + p.off_stats, s);
   if (rc != E2E_OK) return rc;
-  if (p.sweep) return launch_sweep(d, p, logits, targets, in_len, tgt_len, losses, nullptr, 1.0, ws, s);
-  return launch_lattice(d, p, logits, targets, in_len, tgt_len, losses, nullptr, 1.0, ws, s);
+  return launch_fused(d, p, logits, targets, in_len, tgt_len, losses, nullptr, 1.0, ws, s);
 }
 
 // loss + gradient (scale folded in) in as few launches as the shape allows:
@@ -335,14 +218,9 @@ static int loss_forward(const e2e_ctc_desc& d, const LossPlan& p, const void* lo
 static int loss_fwd_bwd(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
                         const void* in_len, const void* tgt_len, void* losses, void* grads, double scale,
                         char* ws, cudaStream_t s) {
-  if (p.wave) {
-    E2E_CUDA_TRY(cudaMemsetAsync(ws + p.off_status, 0, p.off_flags, s));   // status word + the meet flags
-    return launch_wave(d, p, logits, targets, in_len, tgt_len, losses, grads, scale, ws, s);
-  }
   if (p.dense) {
-    E2E_CUDA_TRY(cudaMemsetAsync(ws + p.off_status, 0, 256, s));
-    if (p.sweep) return launch_sweep(d, p, logits, targets, in_len, tgt_len, losses, grads, scale, ws, s);
-    return launch_lattice(d, p, logits, targets, in_len, tgt_len, losses, grads, scale, ws, s);
+    E2E_CUDA_TRY(cudaMemsetAsync(ws + p.off_status, 0, p.off_flags, s));   // status word + the meet flags
+    return launch_fused(d, p, logits, targets, in_len, tgt_len, losses, grads, scale, ws, s);
   }
   int rc = loss_forward(d, p, logits, targets, in_len, tgt_len, losses, ws, s);
   if (rc != E2E_OK) return rc;
@@ -407,9 +285,6 @@ int e2e_ctc_profile_read(double* ms, uint64_t* launches, int32_t n_kinds) {
   g_prof_pending.clear();
   return E2E_OK;
 }
-
-/* debugging aid (not part of the public header): clock stamps recorded with E2E_CTC_TRACE=1 */
-int e2e_ctc_debug_trace_read(long long* host, size_t n) { return lattice_trace_read(host, n); }
 
 int e2e_ctc_get_limits(e2e_ctc_limits* out) {
   if (!out) { set_error("null limits"); return E2E_ERR_INVALID_ARGUMENT; }

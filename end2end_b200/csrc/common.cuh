@@ -10,74 +10,41 @@
 namespace e2e {
 
 // ------------------------------------------------------------------ lattice kernel plan -------
-constexpr int kNumChunks = 4;          // emission / state ring depth, in chunks of 2^chunk_log2 frames
-constexpr int kMaxCombinerWarps = 4;
-constexpr int kMaxProducerWarps = 4;
-constexpr int kMaxCellsPerLane = 40;
-constexpr int kMaxLatticeWarps = 4;    // lattice warps per sweep
-constexpr int kDenseMaxAlphabet = 128; // fused ("dense") mode stages whole rows: <= 4 symbols per producer lane
-constexpr int kNegExp = -(1 << 28);    // block exponent of an all-zero lane
+constexpr int kDenseMaxAlphabet = 128; // fused ("dense") mode stages whole rows by symbol
+constexpr int kNegExp = -(1 << 28);    // block exponent of an all-zero block
 
-struct __align__(16) Boundary {        // cells a lattice warp hands to its neighbour warp (NW > 1)
-  double x0, x1;
-  int e, pad0, pad1, pad2;
-};
-
-// byte offsets of the lattice kernel's dynamic shared memory regions (computed once, on the host)
-struct LatticeSmem {
-  int lab, misc, E, raw, rstat, val, stage, acc, bnd, red, bars, total;
-};
-
-// shared-memory layout of the one-warp-per-sweep lattice kernel (ctc_sweep_impl.cuh), bytes
-struct SweepLayout {
-  int cf, es, rawrow, vpad;
-  int off_lab, off_warp, warp_bytes, w_E, w_raw, w_stat, w_rs, w_acc, w_stage;
-};
-
-constexpr int kWaveCF = 8;       // wave kernel: frames per hand-off chunk
-constexpr int kWaveRB = 32;      // boundary-slot ring depth (frames)
-constexpr int kWavePF = 4;       // stashed rows each combiner warp keeps in flight
-// shared-memory layout and role counts of the wave kernel (ctc_wave_impl.cuh)
-struct WaveLayout {
-  int K, NW;        // cells per lane, lattice warps per sweep
-  int NP, NC;       // producer (row log-softmax) warps, combiner warps
-  int by_smsp;      // lay the roles out by SM sub-partition (warp id % 4): latency configurations
-  int nwarps;       // warps per CTA
-  int nap;          // nanoseconds a waiting producer / combiner warp sleeps between polls (0: spin)
-  int R, RV;        // frames in the emission ring / in the val ring (powers of two)
-  int es;           // doubles per emission-ring frame: V symbols, a zero column, the row normaliser
-  int vpad;         // u32 posterior accumulators per combiner warp
-  int off_lab, off_occ, off_E, off_valw, off_vale, off_stage, off_acc, off_bnd, off_ctl, total;
+// shared-memory layout and role map of the lattice kernel (ctc_fused_impl.cuh), computed once on the host
+struct FzLayout {
+  int NB;          // kernel class: block rows (of four cells) per lane the kernel is instantiated for: 1, 2, 4, 10
+  int gather;      // 1: emissions gathered by label + compact posteriors for K3; 0: dense rows, gradient written in-kernel
+  int NP, NC, PF;  // producer warps, combiner warps, stashed rows each combiner keeps in flight (2 or 4)
+  int nwarps;      // warps per CTA
+  int nap;         // nanoseconds a waiting producer / combiner sleeps between polls
+  int R, RV, CF;   // frames in the emission ring / the val ring (powers of two), frames per ring check
+  int rv_log2, neb_log2, neb_mask;   // log2(RV); emission-ring blocks R / PB: log2 and mask
+  int PB, pb_log2; // frames per producer block (dense: 32, one lane per frame; gather: 8, one warp per frame)
+  int es;          // doubles per emission-ring frame
+  int vframe;      // bytes per val-ring frame
+  int srow;        // bytes per staged stash row
+  int prow;        // floats per combiner posterior row
+  int off_lab, off_occ, off_E, off_val, off_stage, off_post, off_ctl, total;
+  signed char role[16];   // per warp: 0 lattice, 1 combiner, 2 producer, 3 idle
+  signed char ridx[16];   // index within the role
 };
 
 // One forward call leaves everything the backward needs in the caller's workspace.
 struct LossPlan {
-  int wave;         // 1: the wave kernel (ctc_wave_*.cu): fused small-alphabet path
-  WaveLayout wv;
-  size_t off_meet;
-  int sweep;        // 1: one-warp-per-sweep kernel (ctc_sweep_*.cu); 0: the warp-specialised cluster kernel
-  SweepLayout sw;
-  int K;            // lattice cells per lane (even: cells alternate blank,label)
-  int NW;           // lattice warps per sweep
-  int cells;        // 32*K*NW  >= 2*Lmax+1
-  int lanes;        // 32*NW
-  int words;        // u32 words per lane per frame in the state rows: K cells + exponent, padded to 4
-  int dense;        // fused mode: whole rows staged, log-softmax + gradient write inside the lattice kernel
-  int np;           // producer warps per CTA
-  int nc;           // combiner warps per CTA (power of two)
-  int pfd;          // stashed rows each combiner warp keeps in flight (cp.async)
-  int rowlen;       // emissions staged per frame: V (dense) or Lmax+1 (gather)
-  int chunk_log2;   // frames per hand-off = 1 << chunk_log2; the rings hold kNumChunks chunks
-  int lstride;      // doubles per emission-ring frame
-  int post_stride;  // floats per frame of the compact posterior rows (gather mode): cells/2 labels + blank
-  int vpad;         // dense mode: u32 accumulators per frame
-  LatticeSmem sm;
+  FzLayout fz;
+  int dense;        // fused mode: log-softmax + gradient write inside the lattice kernel (alphabet <= kDenseMaxAlphabet)
+  int cells;        // 128 * NB: lattice cells the kernel class covers (>= 2*Lmax+1)
+  int post_stride;  // floats per frame of the compact posterior rows (gather mode): cells/2 labels + blank total
+  int roww;         // u32 words per stash row: 4 cell words + 1 exponent per block, 32*NB blocks
   size_t smem;      // dynamic shared memory of the lattice kernel
   // byte offsets into the workspace
-  size_t off_status, off_flags, off_stats, off_stash, off_post, total;
+  size_t off_status, off_meet, off_flags, off_stats, off_stash, off_post, total;
 };
 
-// fused: the caller wants loss + gradient in one pass (dense mode is used when the shape allows it)
+// fused: the caller wants loss + gradient in one pass (dense mode is used when the alphabet allows it)
 bool make_loss_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p);
 
 // status word bits (device-side argument check)
@@ -201,21 +168,13 @@ __device__ __forceinline__ int warp_max_int(int v) {
 
 // ------------------------------------------------------------------ kernel launchers ----------
 int launch_row_stats(const e2e_ctc_desc& d, const void* logits, void* stats, cudaStream_t s);
-int launch_lattice(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
-                   const void* in_len, const void* tgt_len, void* losses, void* grads, double scale, char* ws,
-                   cudaStream_t s);
+int launch_fused(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
+                 const void* in_len, const void* tgt_len, void* losses, void* grads, double scale, char* ws,
+                 cudaStream_t s);
+size_t fused_ctl_bytes();
 int launch_grad(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
                 const void* in_len, const void* tgt_len, const void* grad_out, int grad_out_count,
                 double host_scale, void* grads, const char* ws, cudaStream_t s);
-int lattice_trace_read(long long* host, size_t n);
-int launch_sweep(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
-                 const void* in_len, const void* tgt_len, void* losses, void* grads, double scale, char* ws,
-                 cudaStream_t s);
-int launch_wave(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
-                const void* in_len, const void* tgt_len, void* losses, void* grads, double scale, char* ws,
-                cudaStream_t s);
-size_t wave_ctl_bytes();
-constexpr int kSweepMaxCellsPerLane = 40;   // one warp covers 32 * 40 = 1280 cells: L <= 639
 int launch_scale_rows(const e2e_ctc_desc& d, void* grads, const void* grad_out, int grad_out_count, cudaStream_t s);
 int launch_reduce(const void* losses, int dtype, int B, double scale, void* out, double* out64,
                   cudaStream_t s);
