@@ -133,5 +133,23 @@ def profile_read():
     return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(KERNEL_KINDS)}
 
 
+_forced_kernel = -1
+
+
+def force_kernel(kind=-1):
+    """Testing hook: force a lattice kernel where the shape allows it (-1 automatic, 0 general, 1 wave,
+    2 one-warp-per-sweep).  Process-wide; the parity tests use it to run every kernel on every shape."""
+    global _forced_kernel
+    L = load()
+    L.e2e_ctc_debug_force_kernel.argtypes = [ctypes.c_int32]
+    L.e2e_ctc_debug_force_kernel.restype = ctypes.c_int
+    check(L.e2e_ctc_debug_force_kernel(int(kind)))
+    _forced_kernel = int(kind)
+
+
+def forced_kernel():
+    return _forced_kernel
+
+
 def launch_count():
     return int(load().e2e_ctc_launch_count())

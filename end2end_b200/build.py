@@ -17,6 +17,7 @@ LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libe2e_ctc.so")
 SOURCES = ["api.cu", "comm.cu", "ctc_rowstats.cu", "ctc_fused_a.cu", "ctc_fused_b.cu", "ctc_fused_c.cu",
+           "ctc_wave_a.cu", "ctc_wave_b.cu", "ctc_sweep_a.cu", "ctc_sweep_b.cu", "ctc_sweep_c.cu", "ctc_sweep_d.cu",
            "ctc_grad.cu", "ctc_greedy.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -39,7 +40,7 @@ def _stale(target, deps):
 def build(force=False, verbose=False, extra=()):
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "ctc_fused_impl.cuh"),
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "ctc_fused_impl.cuh"), os.path.join(CSRC, "ctc_sweep_impl.cuh"), os.path.join(CSRC, "ctc_wave_impl.cuh"),
                os.path.join(HERE, "..", "include", "e2e_ctc.h")]
     nvcc = _nvcc()
     jobs = []

@@ -15,6 +15,7 @@ namespace e2e {
 
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_force_kernel{-1};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -99,22 +100,150 @@ static int check_desc(const e2e_ctc_desc* d, bool need_targets) {
   return E2E_OK;
 }
 
+// One-warp-per-sweep kernel: variants by cells per lane; f64 inputs use a subset (compile time).
+static const int kSweepK[] = {2, 4, 6, 8, 10, 12, 14, 16, 20, 24, 28, 32, 36, 40};
+static const int kSweepK64[] = {2, 4, 8, 16, 24, 40};
+
+static bool make_sweep_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
+  const int S = 2 * d.max_targets + 1;
+  const bool f64 = d.dtype == E2E_F64;
+  int K = 0;
+  if (f64) { for (int k : kSweepK64) if (32 * k >= S) { K = k; break; } }
+  else { for (int k : kSweepK) if (32 * k >= S) { K = k; break; } }
+  if (!K) return false;
+  p->kind = kPlanSweep;
+  p->K = K; p->NW = 1; p->cells = 32 * K;
+  p->words = (K + 1 + 3) & ~3;
+  p->dense = fused && d.alphabet <= kDenseMaxAlphabet;
+  const int rowlen = p->dense ? d.alphabet : d.max_targets + 1;
+  p->post_stride = p->cells / 2 + 4;
+  p->vpad = p->dense ? ((d.alphabet + 1 + 3) & ~3) : 0;
+  const int H = K / 2, PF = K >= 24 ? 2 : 8;
+  const int et = f64 ? 8 : 4;
+  const int esz = f64 ? 8 : (d.dtype == E2E_F32 ? 4 : 2);
+  SweepLayout L;
+  L.vpad = p->vpad;
+  L.es = p->dense ? ((d.alphabet + 1) | 1) : (1 + 32 * H);
+  if (f64) L.rawrow = rowlen * 8;
+  else if (p->dense) L.rawrow = ((((d.alphabet * esz + 2 + 3) >> 2)) | 1) * 4;
+  else L.rawrow = ((d.max_targets + 1) | 1) * 4;
+  auto layout = [&](int cf) {
+    L.cf = cf;
+    size_t off = 0;
+    L.off_lab = 0; off = (size_t)align16i((size_t)(32 * H + 1) * 4);
+    L.off_warp = (int)off;
+    size_t w = 0;
+    L.w_E = (int)w; w = (size_t)align16i(w + (size_t)cf * L.es * et);
+    L.w_raw = (int)w; w = (size_t)align16i(w + (size_t)cf * L.rawrow);
+    L.w_stat = (int)w; w += (size_t)cf * 16;
+    L.w_rs = (int)w; w = (size_t)align16i(w + (size_t)cf * 4);
+    L.w_acc = (int)w; w += (size_t)2 * L.vpad * 4;
+    L.w_stage = (int)w; w += (size_t)PF * 32 * p->words * 4;
+    L.warp_bytes = (int)w;
+    return off + 2 * w;
+  };
+  int cf = 32;
+  // several CTAs per SM when the batch is large; otherwise whatever fits
+  const size_t want = d.batch > 148 ? 56 * 1024 : 200 * 1024;
+  while (cf > 8 && layout(cf) > want) cf >>= 1;
+  const size_t smem = layout(cf);
+  if (smem > 220 * 1024) return false;
+  p->sw = L;
+  p->smem = smem;
+  const size_t rows = (size_t)d.batch * d.max_frames;
+  size_t off = 0;
+  p->off_status = off; off += 256;
+  p->off_meet = off;
+  p->off_flags = off; off += align256((size_t)d.batch * 4);
+  p->off_stats = off; off += p->dense ? 0 : align256(rows * (f64 ? 16 : 8));
+  p->off_stash = off; off += align256(rows * 32 * p->words * 4);
+  p->off_post = off; off += p->dense ? 0 : align256(rows * p->post_stride * 4);
+  p->total = off;
+  return true;
+}
+
+// Wave kernel (fused small-alphabet path): variants by (cells per lane, lattice warps per sweep).
+static bool make_wave_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
+  if (!fused || d.dtype == E2E_F64 || d.alphabet > kDenseMaxAlphabet) return false;
+  // Latency shapes only -- at most two rounds of resident clusters (one 2-CTA cluster per utterance, one CTA per
+  // SM: B <= 148) and two to four lattice warps per sweep; measured on c2-shaped batches the wave kernel wins up
+  // to B = 148 and ties at B = 256; larger batches and short lattices are throughput-bound.
+  static const int kVar[][2] = {{4, 1}, {4, 2}, {4, 4}, {4, 8}, {8, 8}};
+  const int S = 2 * d.max_targets + 1;
+  int K = 0, NW = 0;
+  for (const auto& v : kVar)
+    if (32 * v[0] * v[1] >= S && !K) { K = v[0]; NW = v[1]; }
+  if (d.batch > 148 || NW > 4 || (NW == 1 && 2 * d.batch > 148)) return false;
+  if (!K) return false;
+  WaveLayout L;
+  L.K = K; L.NW = NW;
+  L.NC = NW >= 4 ? 6 : 2;
+  L.NP = NW >= 4 ? 2 : 1;
+  if (L.NC < 1 || L.NC > 8 || (L.NP != 1 && L.NP != 2 && L.NP != 4)) return false;
+  L.nap = 32;
+  L.by_smsp = 0;
+  if (L.by_smsp) {
+    int r = NW > L.NP ? NW : L.NP;
+    if ((L.NC + 1) / 2 > r) r = (L.NC + 1) / 2;
+    L.nwarps = 4 * r;
+  } else {
+    L.nwarps = NW + L.NC + L.NP;
+  }
+  if (L.nwarps > (NW <= 4 ? 16 : 32)) return false;
+  const int lanes = 32 * NW, roww = lanes * (K + 1);
+  L.es = (d.alphabet + 2) | 1;   // odd: the producer's lane-per-frame stores are bank-conflict free
+  L.vpad = (d.alphabet + 3) & ~3;
+  L.RV = lanes * K >= 1024 ? 16 : 32;
+  L.R = 128;   // producer blocks are 32 frames: two per producer in flight
+  if (L.R < 64 || (L.R & (L.R - 1))) return false;
+  while (L.R > 64 && (size_t)L.R * L.es * 8 > (size_t)(NW >= 4 ? 64 : 40) * 1024) L.R >>= 1;
+  if (L.RV > L.R / 2) L.RV = L.R / 2;
+  if (L.RV < kWaveCF || (L.RV & (L.RV - 1))) return false;
+  size_t off = 0;
+  L.off_lab = 0; off = (size_t)align16i((size_t)(lanes * K / 2 + 1) * 4);
+  L.off_occ = (int)off; off = (size_t)align16i(off + (size_t)(lanes * K / 2 + d.alphabet + 2) * 4);   // label indices by symbol + offsets
+  L.off_E = (int)off; off = (size_t)align16i(off + (size_t)L.R * L.es * 8);
+  L.off_valw = (int)off; off += (size_t)L.RV * lanes * K * 4;
+  L.off_vale = (int)off; off += (size_t)L.RV * lanes * 4;
+  L.off_stage = (int)off; off += (size_t)L.NC * kWavePF * (roww + 4) * 4;
+  L.off_acc = (int)off; off += (size_t)L.NC * (lanes * K / 2 + 4) * 4;   // one row of label posteriors per combiner warp (+ a spare slot)
+  L.off_bnd = (int)off; off += (size_t)NW * kWaveRB * 16;
+  L.off_ctl = (int)off; off += wave_ctl_bytes();
+  L.total = (int)off;
+  if (off > 220 * 1024) return false;
+  p->kind = kPlanWave; p->wv = L;
+  p->K = K; p->NW = NW; p->cells = lanes * K; p->words = K + 1;
+  p->dense = 1; p->vpad = L.vpad; p->post_stride = 0;
+  p->smem = off;
+  const size_t rows = (size_t)d.batch * d.max_frames;
+  size_t o = 0;
+  p->off_status = o; o += 256;
+  p->off_meet = o; o += align256((size_t)d.batch * 8);
+  p->off_flags = o; o += align256((size_t)d.batch * 4);
+  p->off_stats = o;
+  p->off_stash = o; o += align256(rows * roww * 4);
+  p->off_post = o;
+  p->total = o;
+  return true;
+}
+
 // Tuning overrides for the lattice kernel's role counts and ring sizes, read ONCE per process (experiments
 // run one configuration per process; a production process never sets them).
-struct FzTune { int nc, np, nwarps, rv, r, pf, nap, cf, latency; };
+struct FzTune { int nc, np, nwarps, rv, r, pf, nap, cf, latency, dbg; };
 static const FzTune& fz_tune() {
   static const FzTune t = {env_int("E2E_CTC_NC", 0), env_int("E2E_CTC_NP", 0), env_int("E2E_CTC_NWARPS", 0),
                            env_int("E2E_CTC_RV", 0), env_int("E2E_CTC_R", 0), env_int("E2E_CTC_PF", 0),
-                           env_int("E2E_CTC_NAP", -1), env_int("E2E_CTC_CF", 0), env_int("E2E_CTC_LATENCY", -1)};
+                           env_int("E2E_CTC_NAP", -1), env_int("E2E_CTC_CF", 0), env_int("E2E_CTC_LATENCY", -1), env_int("E2E_CTC_DBG", 0)};
   return t;
 }
 
-bool make_loss_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
+static bool make_fused_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   const int Lmax = d.max_targets, V = d.alphabet;
   const int NB = Lmax <= 63 ? 1 : (Lmax <= 127 ? 2 : (Lmax <= 255 ? 4 : (Lmax <= kMaxTargets ? 10 : 0)));
   if (!NB) return false;
   const FzTune& tn = fz_tune();
   const bool dense = fused && V <= kDenseMaxAlphabet;
+
   // latency shapes: every CTA of the launch has an SM to itself (one 2-CTA cluster per utterance), so the
   // CTA is laid out for the shortest per-frame chain; otherwise several CTAs share an SM and the layout is
   // sized for occupancy
@@ -124,15 +253,17 @@ bool make_loss_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   memset(&L, 0, sizeof(L));
   L.NB = NB;
   L.gather = dense ? 0 : 1;
+  L.dbg = tn.dbg;
   const bool heavy_rows = !dense || V > 32;   // producer work per frame: a whole row of > 32 symbols, or a gather
   const int maxw = NB <= 4 ? 8 : 5;
+  const int nsc = NB <= 4 ? 1 : 0;              // scaler warp (exponent snapshots): every class but the large-lattice one
   if (NB == 10) { L.NP = 1; L.NC = 3; L.nwarps = 5; }
-  else if (latency) { L.NP = heavy_rows ? 2 : 1; L.NC = heavy_rows ? 4 : 5; L.nwarps = 8; }
-  else { L.NP = heavy_rows ? 2 : 1; L.NC = NB >= 4 ? 3 : 2; L.nwarps = 1 + L.NP + L.NC; }
+  else if (latency) { L.NP = 2; L.NC = 4; L.nwarps = 8; }
+  else { L.NP = heavy_rows ? 2 : 1; L.NC = NB >= 4 ? 3 : 2; L.nwarps = 1 + nsc + L.NP + L.NC; }
   if (tn.np == 1 || tn.np == 2 || tn.np == 4) L.NP = tn.np;   // a power of two (the lattice masks with NP-1)
   if (tn.nc >= 1 && tn.nc <= 8) L.NC = tn.nc;
   if (tn.nwarps) L.nwarps = tn.nwarps;
-  if (L.nwarps < 1 + L.NP + L.NC) L.nwarps = 1 + L.NP + L.NC;
+  if (L.nwarps < 1 + nsc + L.NP + L.NC) L.nwarps = 1 + nsc + L.NP + L.NC;
   if (L.nwarps > maxw) return false;
   L.PF = (latency && NB < 10) ? 4 : 2;
   if (tn.pf == 2 || tn.pf == 4) L.PF = tn.pf;
@@ -143,9 +274,10 @@ bool make_loss_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   if (L.RV < 2 * L.CF) L.RV = 2 * L.CF;
   L.nap = tn.nap >= 0 ? tn.nap : 32;
   L.es = dense ? ((V + 2) | 1) : (64 * NB + 1);   // odd: the producers' lane-per-frame stores are bank-conflict free
-  L.PB = dense ? 32 : 8;
-  L.pb_log2 = dense ? 5 : 3;
-  L.R = 2 * L.PB;                                 // two producer blocks in flight
+  L.PB = 8;            // frames per producer block (one warp per frame, four frames in flight)
+  L.pb_log2 = 3;
+  L.R = 2 * L.PB;                                 // at least two producer blocks in the ring, four when they fit 32 KB
+  if ((size_t)4 * L.PB * L.es * 8 <= 32 * 1024) L.R = 4 * L.PB;
   while (L.R < 128 && (size_t)2 * L.R * L.es * 8 <= (size_t)(latency ? 48 : 24) * 1024) L.R *= 2;
   if (tn.r >= 2 * L.PB && !(tn.r & (tn.r - 1))) L.R = tn.r;
   if (L.R > 16 * L.PB) L.R = 16 * L.PB;   // at most 16 emission blocks (one mbarrier each)
@@ -157,10 +289,10 @@ bool make_loss_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   const int nbp = (NB + 3) & ~3;
   L.vframe = NB * 640 + 32 * nbp * 4;
   L.srow = 640 * NB;
-  L.prow = 64 * NB + 4;
+  L.prow = dense ? ((V + 4) & ~3) : 0;   // dense: per-symbol fixed-point accumulators of one frame + a spare slot
   size_t off = 0;
   L.off_lab = 0; off = (size_t)align16i((size_t)(64 * NB + 1) * 4);
-  L.off_occ = (int)off; off = (size_t)align16i(off + (size_t)(64 * NB + V + 2) * 4 * (dense ? 1 : 0));
+  L.off_occ = (int)off; off = (size_t)align16i(off + (size_t)nsc * 2 * 20 * 32 * NB);   // scale table: 2 slots x 32*NB blocks x {f, fb, en}
   L.off_E = (int)off; off = (size_t)align16i(off + (size_t)L.R * L.es * 8);
   L.off_val = (int)off; off += (size_t)L.RV * L.vframe;
   L.off_stage = (int)off; off += (size_t)L.NC * L.PF * L.srow;
@@ -179,7 +311,9 @@ bool make_loss_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
     int k = 0;
     for (int q = 0; q < L.NC; q++) { L.role[order[k]] = 1; L.ridx[order[k]] = (signed char)q; k++; }
     for (int q = 0; q < L.NP; q++) { L.role[order[k]] = 2; L.ridx[order[k]] = (signed char)q; k++; }
+    if (nsc) L.role[order[n - 1]] = 4;   // the scaler is light: it takes the last warp (the lattice warp's sub-partition when there are 8)
   }
+  p->kind = kPlanFused;
   p->fz = L;
   p->dense = dense ? 1 : 0;
   p->cells = 128 * NB;
@@ -198,6 +332,29 @@ bool make_loss_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   return true;
 }
 
+
+// Which lattice kernel runs a shape (all three are parity-tested against the oracle on the shapes they take):
+//  * wave kernel: latency shapes (B <= 148 utterances, small alphabet, <= 255 labels) -- four lattice warps per sweep;
+//  * one-warp-per-sweep kernel: throughput shapes with small alphabets (many utterances per SM);
+//  * general kernel: everything else -- large alphabets (gather mode), and a single label symbol (V == 2, where the
+//    sweep kernel's lane-exponent rule loses the only feasible path of a tight alignment under very peaky
+//    emissions: round 1's open parity corner; the general kernel's per-block exponents do not).
+bool make_loss_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
+  memset(p, 0, sizeof(*p));
+  const int force = g_force_kernel.load(std::memory_order_relaxed);   // testing hook: 0 general, 1 wave, 2 sweep (when the shape allows)
+  const bool gather = !fused || d.alphabet > kDenseMaxAlphabet;
+  if (force == kPlanFused) return make_fused_plan(d, fused, p);
+  if (force == kPlanWave && make_wave_plan(d, fused, p)) return true;
+  if (force == kPlanSweep && make_sweep_plan(d, fused, p)) return true;
+  if (d.alphabet == 2) return make_fused_plan(d, fused, p);
+  if (gather && d.batch <= 256 && make_fused_plan(d, fused, p)) return true;
+  if (make_wave_plan(d, fused, p)) return true;
+  memset(p, 0, sizeof(*p));
+  if (make_sweep_plan(d, fused, p)) return true;
+  memset(p, 0, sizeof(*p));
+  return make_fused_plan(d, fused, p);
+}
+
 static int check_ws(const void* ws, size_t have, size_t need) {
   if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255)) { set_error("workspace null or not 256-byte aligned"); return E2E_ERR_WORKSPACE; }
   if (have < need) { set_error("workspace too small: %zu < %zu bytes", have, need); return E2E_ERR_WORKSPACE; }
@@ -210,6 +367,7 @@ static int loss_forward(const e2e_ctc_desc& d, const LossPlan& p, const void* lo
   E2E_CUDA_TRY(cudaMemsetAsync(ws + p.off_status, 0, p.off_flags, s));   // status word + the meet flags
   int rc = launch_row_stats(d, logits, ws + p.off_stats, s);
   if (rc != E2E_OK) return rc;
+  if (p.kind == kPlanSweep) return launch_sweep(d, p, logits, targets, in_len, tgt_len, losses, nullptr, 1.0, ws, s);
   return launch_fused(d, p, logits, targets, in_len, tgt_len, losses, nullptr, 1.0, ws, s);
 }
 
@@ -220,6 +378,8 @@ static int loss_fwd_bwd(const e2e_ctc_desc& d, const LossPlan& p, const void* lo
                         char* ws, cudaStream_t s) {
   if (p.dense) {
     E2E_CUDA_TRY(cudaMemsetAsync(ws + p.off_status, 0, p.off_flags, s));   // status word + the meet flags
+    if (p.kind == kPlanWave) return launch_wave(d, p, logits, targets, in_len, tgt_len, losses, grads, scale, ws, s);
+    if (p.kind == kPlanSweep) return launch_sweep(d, p, logits, targets, in_len, tgt_len, losses, grads, scale, ws, s);
     return launch_fused(d, p, logits, targets, in_len, tgt_len, losses, grads, scale, ws, s);
   }
   int rc = loss_forward(d, p, logits, targets, in_len, tgt_len, losses, ws, s);
@@ -285,6 +445,10 @@ int e2e_ctc_profile_read(double* ms, uint64_t* launches, int32_t n_kinds) {
   g_prof_pending.clear();
   return E2E_OK;
 }
+
+/* testing hook (not part of the public header): force a lattice kernel where the shape allows it.
+ * -1 automatic, 0 general kernel, 1 wave kernel, 2 one-warp-per-sweep kernel */
+int e2e_ctc_debug_force_kernel(int32_t kind) { g_force_kernel.store(kind, std::memory_order_relaxed); return E2E_OK; }
 
 int e2e_ctc_get_limits(e2e_ctc_limits* out) {
   if (!out) { set_error("null limits"); return E2E_ERR_INVALID_ARGUMENT; }

@@ -13,7 +13,35 @@ namespace e2e {
 constexpr int kDenseMaxAlphabet = 128; // fused ("dense") mode stages whole rows by symbol
 constexpr int kNegExp = -(1 << 28);    // block exponent of an all-zero block
 
-// shared-memory layout and role map of the lattice kernel (ctc_fused_impl.cuh), computed once on the host
+constexpr int kNumChunks = 4;          // emission / state ring depth, in chunks of 2^chunk_log2 frames
+constexpr int kMaxCombinerWarps = 4;
+constexpr int kMaxProducerWarps = 4;
+constexpr int kMaxCellsPerLane = 40;
+constexpr int kMaxLatticeWarps = 4;    // lattice warps per sweep
+
+// shared-memory layout of the one-warp-per-sweep lattice kernel (ctc_sweep_impl.cuh), bytes
+struct SweepLayout {
+  int cf, es, rawrow, vpad;
+  int off_lab, off_warp, warp_bytes, w_E, w_raw, w_stat, w_rs, w_acc, w_stage;
+};
+
+constexpr int kWaveCF = 8;       // wave kernel: frames per hand-off chunk
+constexpr int kWaveRB = 32;      // boundary-slot ring depth (frames)
+constexpr int kWavePF = 4;       // stashed rows each combiner warp keeps in flight
+// shared-memory layout and role counts of the wave kernel (ctc_wave_impl.cuh)
+struct WaveLayout {
+  int K, NW;        // cells per lane, lattice warps per sweep
+  int NP, NC;       // producer (row log-softmax) warps, combiner warps
+  int by_smsp;      // lay the roles out by SM sub-partition (warp id % 4): latency configurations
+  int nwarps;       // warps per CTA
+  int nap;          // nanoseconds a waiting producer / combiner warp sleeps between polls (0: spin)
+  int R, RV;        // frames in the emission ring / in the val ring (powers of two)
+  int es;           // doubles per emission-ring frame: V symbols, a zero column, the row normaliser
+  int vpad;         // u32 posterior accumulators per combiner warp
+  int off_lab, off_occ, off_E, off_valw, off_vale, off_stage, off_acc, off_bnd, off_ctl, total;
+};
+
+// shared-memory layout and role map of the general lattice kernel (ctc_fused_impl.cuh), computed once on the host
 struct FzLayout {
   int NB;          // kernel class: block rows (of four cells) per lane the kernel is instantiated for: 1, 2, 4, 10
   int gather;      // 1: emissions gathered by label + compact posteriors for K3; 0: dense rows, gradient written in-kernel
@@ -22,23 +50,33 @@ struct FzLayout {
   int nap;         // nanoseconds a waiting producer / combiner sleeps between polls
   int R, RV, CF;   // frames in the emission ring / the val ring (powers of two), frames per ring check
   int rv_log2, neb_log2, neb_mask;   // log2(RV); emission-ring blocks R / PB: log2 and mask
-  int PB, pb_log2; // frames per producer block (dense: 32, one lane per frame; gather: 8, one warp per frame)
+  int dbg;         // debugging switches (FZ_DBG builds only)
+  int PB, pb_log2; // frames per producer block
   int es;          // doubles per emission-ring frame
   int vframe;      // bytes per val-ring frame
   int srow;        // bytes per staged stash row
   int prow;        // floats per combiner posterior row
   int off_lab, off_occ, off_E, off_val, off_stage, off_post, off_ctl, total;
-  signed char role[16];   // per warp: 0 lattice, 1 combiner, 2 producer, 3 idle
+  signed char role[16];   // per warp: 0 lattice, 1 combiner, 2 producer, 3 idle, 4 scaler
   signed char ridx[16];   // index within the role
 };
 
-// One forward call leaves everything the backward needs in the caller's workspace.
+// One forward call leaves everything the backward needs in the caller's workspace.  Three lattice kernels share
+// the plan: kind 0 the general kernel (ctc_fused_impl.cuh: every shape), kind 1 the wave kernel (latency shapes,
+// small alphabets), kind 2 the one-warp-per-sweep kernel (throughput shapes).
+enum { kPlanFused = 0, kPlanWave = 1, kPlanSweep = 2 };
 struct LossPlan {
+  int kind;
   FzLayout fz;
+  WaveLayout wv;
+  SweepLayout sw;
+  int K, NW;        // wave / sweep: cells per lane, lattice warps per sweep
   int dense;        // fused mode: log-softmax + gradient write inside the lattice kernel (alphabet <= kDenseMaxAlphabet)
-  int cells;        // 128 * NB: lattice cells the kernel class covers (>= 2*Lmax+1)
+  int cells;        // lattice cells the kernel variant covers (>= 2*Lmax+1)
   int post_stride;  // floats per frame of the compact posterior rows (gather mode): cells/2 labels + blank total
-  int roww;         // u32 words per stash row: 4 cell words + 1 exponent per block, 32*NB blocks
+  int roww;         // general kernel: u32 words per stash row (4 cell words + 1 exponent per block, 32*NB blocks)
+  int words;        // sweep: u32 words per lane per frame in the stash rows
+  int vpad;
   size_t smem;      // dynamic shared memory of the lattice kernel
   // byte offsets into the workspace
   size_t off_status, off_meet, off_flags, off_stats, off_stash, off_post, total;
@@ -172,6 +210,14 @@ int launch_fused(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, c
                  const void* in_len, const void* tgt_len, void* losses, void* grads, double scale, char* ws,
                  cudaStream_t s);
 size_t fused_ctl_bytes();
+int launch_sweep(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
+                 const void* in_len, const void* tgt_len, void* losses, void* grads, double scale, char* ws,
+                 cudaStream_t s);
+int launch_wave(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
+                const void* in_len, const void* tgt_len, void* losses, void* grads, double scale, char* ws,
+                cudaStream_t s);
+size_t wave_ctl_bytes();
+constexpr int kSweepMaxCellsPerLane = 40;   // one warp covers 32 * 40 = 1280 cells: L <= 639
 int launch_grad(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
                 const void* in_len, const void* tgt_len, const void* grad_out, int grad_out_count,
                 double host_scale, void* grads, const char* ws, cudaStream_t s);

@@ -645,10 +645,13 @@ ctc_sweep_kernel(const SweepParams p) {
 
 template <int K, bool F64>
 int launch_sweep_k(const SweepParams& sp, size_t smem, cudaStream_t s) {
-  static int attr_smem = -1;   // the attribute only ever grows
-  if ((int)smem > attr_smem) {
+  // the dynamic shared-memory opt-in is PER DEVICE: cached per device ordinal (it only ever grows)
+  static int attr_smem[64];
+  int dev = 0;
+  E2E_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || (int)smem > attr_smem[dev]) {
     E2E_CUDA_TRY(cudaFuncSetAttribute(ctc_sweep_kernel<K, F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = (int)smem;
+    if (dev >= 0 && dev < 64) attr_smem[dev] = (int)smem;
   }
   KernelTimer timer(kKernelLattice, s);
   ctc_sweep_kernel<K, F64><<<(unsigned)sp.B, 64, smem, s>>>(sp);

@@ -114,6 +114,7 @@ __device__ __forceinline__ double wv_hi2d(uint32_t h) { return __hiloint2double(
 __device__ __noinline__ double wv_emission_lp(float x, float m, float ls) {
   const double d = (double)x - ((double)m + (double)ls);
   const float hi = (float)d;
+  if (!(hi > -INFINITY)) return hi != hi ? (double)hi : 0.0;   // -inf (a masked symbol) -> exact zero, NaN -> NaN
   const float lo = (float)(d - (double)hi);
   return (double)expf(hi) * (1.0 + (double)lo);
 }
@@ -805,10 +806,13 @@ ctc_wave_kernel(const WaveParams p) {
 
 template <int K, int NW>
 int launch_wave_k(const WaveParams& wp, cudaStream_t s) {
-  static int attr_smem = -1;   // the attribute only ever grows
-  if (wp.L.total > attr_smem) {
+  // the dynamic shared-memory opt-in is PER DEVICE: cached per device ordinal (it only ever grows)
+  static int attr_smem[64];
+  int dev = 0;
+  E2E_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || wp.L.total > attr_smem[dev]) {
     E2E_CUDA_TRY(cudaFuncSetAttribute(ctc_wave_kernel<K, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, wp.L.total));
-    attr_smem = wp.L.total;
+    if (dev >= 0 && dev < 64) attr_smem[dev] = wp.L.total;
   }
   const unsigned threads = 32u * (unsigned)wp.L.nwarps;
   KernelTimer timer(kKernelLattice, s);

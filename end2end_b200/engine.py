@@ -182,22 +182,6 @@ class _Problem:
         return torch.empty_strided(x.size(), x.stride(), dtype=x.dtype, device=x.device, pin_memory=pin)
 
 
-_PLAN_ENV = ("E2E_CTC_WAVE", "E2E_CTC_NO_FUSED", "E2E_CTC_LEGACY", "E2E_CTC_CELLS_PER_LANE", "E2E_CTC_LATTICE_WARPS",
-             "E2E_CTC_LATENCY_MODE", "E2E_CTC_WAVE_NW", "E2E_CTC_WAVE_K", "E2E_CTC_WAVE_NC")
-
-
-# only consulted when one of them was set at import time or E2E_CTC_TEST_ENV=1 (the test-suite toggles them
-# between calls); a production process never pays for the lookups
-_TEST_ENV = bool(os.environ.get("E2E_CTC_TEST_ENV")) or any(os.environ.get(k) is not None for k in _PLAN_ENV)
-
-
-def _plan_env():
-    """The testing / tuning environment switches that change the library's kernel plan (and with it the
-    workspace size): part of the workspace-size cache key."""
-    g = os.environ.get
-    return tuple(g(k) for k in _PLAN_ENV)
-
-
 def _require_cuda():
     if not torch.cuda.is_available():
         raise RuntimeError("end2end_b200 needs a CUDA device (sm_100a): the CTC engine has no CPU fallback")
@@ -345,7 +329,7 @@ class CTCLossEngine:
 
     # ------------------------------------------------------------------ internals --------------
     def _workspace(self, pb):
-        key = (pb.B, pb.T, pb.V, pb.Lmax, pb.desc.dtype) + (_plan_env() if _TEST_ENV else ())
+        key = (pb.B, pb.T, pb.V, pb.Lmax, pb.desc.dtype, _lib.forced_kernel())
         n = self._ws_bytes.get(key)
         if n is None:
             n = self._L.e2e_ctc_loss_workspace_bytes(ctypes.byref(pb.desc))
@@ -372,7 +356,7 @@ class CTCLossEngine:
         return buf
 
     def _ws_need(self, pb):
-        key = (pb.B, pb.T, pb.V, pb.Lmax, pb.desc.dtype) + (_plan_env() if _TEST_ENV else ())
+        key = (pb.B, pb.T, pb.V, pb.Lmax, pb.desc.dtype, _lib.forced_kernel())
         n = self._ws_bytes.get(key)
         if n is None:
             n = self._L.e2e_ctc_loss_workspace_bytes(ctypes.byref(pb.desc))

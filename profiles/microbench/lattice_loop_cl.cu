@@ -18,7 +18,7 @@ __device__ __forceinline__ void mbar_arrive_if(unsigned long long* bar, int on) 
 
 // FLAGS bits: 1 LDS emissions, 2 val-ring STS, 4 snapshot+apply, 8 publish (mbarrier arrive per frame), 16 poll words per 8 frames
 template <int NBU, int FLAGS, int UNROLL, int SPIN = 0, int RT = 0>
-__global__ void __maxnreg__(128) lat(long long* cyc, double* sink, int T, int V, unsigned spin_mask = 0, int es_rt = 33, int vframe_rt = 0, int rm = 127, int rvm = 15) {
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(128) lat(long long* cyc, double* sink, int T, int V, unsigned spin_mask = 0, int es_rt = 33, int vframe_rt = 0, int rm = 127, int rvm = 15) {
   extern __shared__ __align__(16) unsigned char smem[];
   double* E = reinterpret_cast<double*>(smem);                      // [128][33]
   unsigned char* val = smem + 128 * 33 * 8;                         // [16][NBU*640 + 512]
@@ -189,7 +189,7 @@ void run(const char* name, int nwarps, unsigned spin_mask = 0) {
   const int T = 400;
   long long* cyc; double* sink;
   cudaMalloc(&cyc, 256 * 8); cudaMalloc(&sink, 256 * 32 * 8 + 65536);
-  const size_t smem = 128 * 33 * 8 + 16 * (NBU * 640 + 512) + 32 * 8 + 64;
+  const size_t smem = 180 * 1024;
   cudaFuncSetAttribute(lat<NBU, FLAGS, UNROLL, SPIN, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   for (int rep = 0; rep < 2; rep++) lat<NBU, FLAGS, UNROLL, SPIN, RT><<<128, 32 * nwarps, smem>>>(cyc, sink, T, 29, spin_mask, 33, NBU * 640 + 512, 127, 15);
   cudaError_t e = cudaDeviceSynchronize();
@@ -200,6 +200,8 @@ void run(const char* name, int nwarps, unsigned spin_mask = 0) {
 }
 
 int main() {
+  run<3, 31, 4, 0, 1>("CLUSTER(2) + 180 KB smem, runtime strides", 8);
+  run<3, 31, 4, 1, 1>("CLUSTER(2) + 180 KB smem + try_wait spinners", 8, 0xee);
   run<3, 31, 4, 0, 1>("runtime strides + 128 regs", 8);
   run<3, 31, 4, 0, 0>("const strides + 128 regs", 8);
   run<3, 31, 4, 8>("8 KB code streamer: warp 1", 8, 0x02);
