@@ -5,10 +5,11 @@ Hot path only: CTC loss forward+backward and greedy CTC decoding, as hand-writte
 """
 from .decoders.ctc_decoder import CTCDecoder, CTCDecoderError, DecoderResults
 from .encoders.text_encoders import CTCEncoder
-from .engine import CTCGreedyEngine, CTCLossEngine
+from .engine import CTCGreedyEngine, CTCLossEngine, GraphedStep
 from .functions.forward_backward import ForwardBackwardLossFunction
-from .modules.ctc_loss import CTCLoss, ForwardBackwardLossBase
+from .modules.ctc_loss import CTCLoss, ForwardBackwardLossBase, GraphedCTCStep
 
 __all__ = ["CTCLoss", "CTCDecoder", "CTCEncoder", "CTCLossEngine", "CTCGreedyEngine",
-           "ForwardBackwardLossFunction", "ForwardBackwardLossBase", "CTCDecoderError", "DecoderResults"]
+           "ForwardBackwardLossFunction", "ForwardBackwardLossBase", "CTCDecoderError", "DecoderResults",
+           "GraphedStep", "GraphedCTCStep"]
 __version__ = "0.1.0"

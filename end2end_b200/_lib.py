@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libe2e_ctc.so")
+# E2E_CTC_LIB: developer hook -- load an experiment build of the SAME library (python -m end2end_b200.build --tag X)
+LIB_PATH = os.environ.get("E2E_CTC_LIB") or os.path.join(_HERE, "lib", "libe2e_ctc.so")
 
 E2E_OK = 0
 E2E_ERR_LENGTHS = 5
@@ -24,6 +25,7 @@ EXPORTS = (
     "e2e_ctc_engine_greedy_host", "e2e_ctc_engine_last_traffic", "e2e_ctc_launch_count",
     "e2e_ctc_profile_enable", "e2e_ctc_profile_read",
     "e2e_ctc_comm_unique_id", "e2e_ctc_comm_create", "e2e_ctc_comm_destroy", "e2e_ctc_comm_allreduce_sum",
+    "e2e_ctc_graph_create", "e2e_ctc_graph_launch", "e2e_ctc_graph_destroy",
 )
 KERNEL_KINDS = ("row_stats", "lattice", "gradient", "loss_reduce", "argmax", "collapse", "scale_rows")
 
@@ -97,6 +99,12 @@ def load():
     L.e2e_ctc_comm_destroy.argtypes = [vp]
     L.e2e_ctc_comm_destroy.restype = None
     L.e2e_ctc_comm_allreduce_sum.argtypes = [vp, vp, ctypes.c_int64, i32, vp]
+    L.e2e_ctc_graph_create.argtypes = [dp, vp, vp, vp, vp, vp, vp, dbl, vp, vp, dbl, vp, sz, vp, ctypes.POINTER(vp)]
+    L.e2e_ctc_graph_launch.argtypes = [vp, vp]
+    L.e2e_ctc_graph_destroy.argtypes = [vp]
+    L.e2e_ctc_graph_destroy.restype = None
+    for name in ("e2e_ctc_graph_create", "e2e_ctc_graph_launch"):
+        getattr(L, name).restype = ctypes.c_int
     for name in ("e2e_ctc_comm_unique_id", "e2e_ctc_comm_create", "e2e_ctc_comm_allreduce_sum"):
         getattr(L, name).restype = ctypes.c_int
     for name in ("e2e_ctc_get_limits", "e2e_ctc_loss_forward_device", "e2e_ctc_loss_backward_device",

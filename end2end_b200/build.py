@@ -37,16 +37,19 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, extra=()):
+def build(force=False, verbose=False, extra=(), tag=None):
+    """``tag``: an experiment build (own object directory, lib/libe2e_ctc_<tag>.so; load it with E2E_CTC_LIB=<path>)."""
+    objdir = os.path.join(OBJDIR, tag) if tag else OBJDIR
+    lib = os.path.join(LIBDIR, "libe2e_ctc_%s.so" % tag) if tag else LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    os.makedirs(OBJDIR, exist_ok=True)
+    os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "ctc_fused_impl.cuh"), os.path.join(CSRC, "ctc_sweep_impl.cuh"), os.path.join(CSRC, "ctc_wave_impl.cuh"),
                os.path.join(HERE, "..", "include", "e2e_ctc.h")]
     nvcc = _nvcc()
     jobs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+        o = os.path.join(objdir, src.replace(".cu", ".o"))
         if force or _stale(o, [s] + headers):
             jobs.append([nvcc, *ARCH, *FLAGS, *extra, *os.environ.get("E2E_BUILD_EXTRA", "").split(), "-c", s, "-o", o])
 
@@ -61,12 +64,13 @@ def build(force=False, verbose=False, extra=()):
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         list(ex.map(run, jobs))
-    objs = [os.path.join(OBJDIR, s.replace(".cu", ".o")) for s in SOURCES]
-    if force or jobs or _stale(LIB, objs):
-        run([nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-ldl"])
-    return LIB
+    objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in SOURCES]
+    if force or jobs or _stale(lib, objs):
+        run([nvcc, *ARCH, "-shared", "-o", lib, *objs, "-ldl"])
+    return lib
 
 
 if __name__ == "__main__":
+    _tag = sys.argv[sys.argv.index("--tag") + 1] if "--tag" in sys.argv else None
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv,
-                extra=("-Xptxas", "-v") if "--ptxas" in sys.argv else ()))
+                extra=("-Xptxas", "-v") if "--ptxas" in sys.argv else (), tag=_tag))

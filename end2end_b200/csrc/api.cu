@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -33,8 +34,11 @@ static std::atomic<int> g_prof_on{0};
 static std::vector<EventPair> g_prof_pending;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_free;
 static thread_local EventPair t_open{nullptr, nullptr, -1};
+static thread_local int t_capturing = 0;       // a CUDA-graph capture is in progress on this thread: count, do not time
+static thread_local uint64_t t_captured = 0;
 
 void launch_begin(int kind, cudaStream_t s) {
+  if (t_capturing) { t_captured++; return; }       // the graph's launches are counted when the graph is launched
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (!g_prof_on.load(std::memory_order_relaxed)) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -587,6 +591,78 @@ int e2e_ctc_greedy_decode_device(const e2e_ctc_desc* desc, const void* logits, c
                        reinterpret_cast<char*>(workspace), reinterpret_cast<cudaStream_t>(cuda_stream));
 }
 
+// ---- CUDA-graph step ------------------------------------------------------------------------------
+// the whole training step of the loss -- status/meet memset, lattice kernel(s), loss reduction and
+// (multi-GPU) the scalar all-reduce -- captured ONCE for a fixed set of buffers and replayed with one
+// cudaGraphLaunch: the step costs the host ~one driver call instead of 3-5 launches plus their argument marshalling.
+}  // extern "C"
+
+struct e2e_ctc_graph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  uint64_t kernels = 0;       // kernels of this library inside the graph (launch accounting)
+  int device = 0;
+};
+
+extern "C" {
+
+int e2e_ctc_graph_create(const e2e_ctc_desc* desc, const void* logits, const void* targets, const void* logits_lengths,
+                         const void* targets_lengths, void* losses, void* grads, double grad_scale, void* reduced,
+                         double* reduced_f64, double reduce_scale, void* workspace, size_t workspace_bytes,
+                         e2e_ctc_comm* comm, e2e_ctc_graph** out) {
+  if (!out) { set_error("null out pointer"); return E2E_ERR_INVALID_ARGUMENT; }
+  *out = nullptr;
+  if (comm && !reduced) { set_error("graph: the all-reduce needs the reduced-loss buffer"); return E2E_ERR_INVALID_ARGUMENT; }
+  e2e_ctc_graph* g = new (std::nothrow) e2e_ctc_graph();
+  if (!g) { set_error("out of host memory"); return E2E_ERR_CUDA; }
+  cudaStream_t cs = nullptr;
+  cudaError_t ce = cudaGetDevice(&g->device);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+  if (ce != cudaSuccess) { set_error("graph: %s", cudaGetErrorString(ce)); delete g; return E2E_ERR_CUDA; }
+  // a first plain run on the capture stream: one-time attribute opt-ins and lazy module loading must not
+  // happen inside the capture (and argument errors surface here, outside it)
+  int rc = step_impl(desc, logits, targets, logits_lengths, targets_lengths, losses, grads, grad_scale, reduced,
+                     reduced_f64, reduce_scale, workspace, workspace_bytes, cs);
+  if (rc == E2E_OK && cudaStreamSynchronize(cs) != cudaSuccess) { set_error("graph: warm-up run failed"); rc = E2E_ERR_CUDA; }
+  if (rc != E2E_OK) { cudaStreamDestroy(cs); delete g; return rc; }
+  ce = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+  if (ce != cudaSuccess) { set_error("cudaStreamBeginCapture: %s", cudaGetErrorString(ce)); cudaStreamDestroy(cs); delete g; return E2E_ERR_CUDA; }
+  t_capturing = 1; t_captured = 0;
+  rc = step_impl(desc, logits, targets, logits_lengths, targets_lengths, losses, grads, grad_scale, reduced,
+                 reduced_f64, reduce_scale, workspace, workspace_bytes, cs);
+  if (rc == E2E_OK && comm) rc = e2e_ctc_comm_allreduce_sum(comm, reduced, 1, desc->dtype, cs);
+  t_capturing = 0;
+  g->kernels = t_captured;
+  ce = cudaStreamEndCapture(cs, &g->graph);
+  if (rc == E2E_OK && ce != cudaSuccess) { set_error("cudaStreamEndCapture: %s", cudaGetErrorString(ce)); rc = E2E_ERR_CUDA; }
+  if (rc == E2E_OK) {
+    ce = cudaGraphInstantiate(&g->exec, g->graph, 0);
+    if (ce != cudaSuccess) { set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ce)); rc = E2E_ERR_CUDA; }
+  }
+  cudaStreamDestroy(cs);
+  if (rc != E2E_OK) {
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+    return rc;
+  }
+  *out = g;
+  return E2E_OK;
+}
+
+int e2e_ctc_graph_launch(e2e_ctc_graph* g, void* cuda_stream) {
+  if (!g || !g->exec) { set_error("null graph"); return E2E_ERR_INVALID_ARGUMENT; }
+  E2E_CUDA_TRY(cudaGraphLaunch(g->exec, reinterpret_cast<cudaStream_t>(cuda_stream)));
+  g_launches.fetch_add(g->kernels, std::memory_order_relaxed);
+  return E2E_OK;
+}
+
+void e2e_ctc_graph_destroy(e2e_ctc_graph* g) {
+  if (!g) return;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  delete g;
+}
+
 // ---- engine ---------------------------------------------------------------------------------------
 int e2e_ctc_engine_create(int32_t device, e2e_ctc_engine** out) {
   if (!out) { set_error("null out pointer"); return E2E_ERR_INVALID_ARGUMENT; }
@@ -733,6 +809,16 @@ int e2e_ctc_engine_loss_host(e2e_ctc_engine* e, const e2e_ctc_desc* desc, const 
   const size_t row_b = (size_t)d.max_frames * d.alphabet * es;            // bytes of one utterance's logits
   const size_t tg_b = (size_t)d.max_targets * (d.targets_itype == E2E_I64 ? 8 : 4);
   const size_t len_b = d.lengths_itype == E2E_I64 ? 8 : 4;
+  // E2E_CTC_HOST_TRACE=1: device timeline of this call (timing events on the three stages) + host issue times, to stderr
+  static const int trace = env_int("E2E_CTC_HOST_TRACE", 0);
+  cudaEvent_t tr[4 * e2e_ctc_engine::kMaxChunks + 2] = {};
+  double host_us[e2e_ctc_engine::kMaxChunks + 2] = {};
+  auto now_us = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+  const double host_t0 = now_us();
+  if (trace) {
+    for (cudaEvent_t& ev : tr) cudaEventCreate(&ev);
+    cudaEventRecord(tr[4 * nch], e->s_in);
+  }
   if (n_tgt) E2E_CUDA_TRY(cudaMemcpyAsync(e->targets.p, targets, n_tgt, cudaMemcpyHostToDevice, e->s_in));
   E2E_CUDA_TRY(cudaMemcpyAsync(e->in_len.p, logits_lengths, n_len, cudaMemcpyHostToDevice, e->s_in));
   E2E_CUDA_TRY(cudaMemcpyAsync(e->tgt_len.p, targets_lengths, n_len, cudaMemcpyHostToDevice, e->s_in));
@@ -744,17 +830,34 @@ int e2e_ctc_engine_loss_host(e2e_ctc_engine* e, const e2e_ctc_desc* desc, const 
     E2E_CUDA_TRY(cudaEventRecord(e->ev_in[k], e->s_in));
     cudaStream_t sc = e->s_comp[k % e2e_ctc_engine::kComputeStreams];
     E2E_CUDA_TRY(cudaStreamWaitEvent(sc, e->ev_in[k], 0));
+    if (trace) { cudaEventRecord(tr[4 * k], e->s_in); cudaEventRecord(tr[4 * k + 1], sc); }
     rc = loss_fwd_bwd(cd[k], cp[k], dl, reinterpret_cast<char*>(e->targets.p) + b0 * tg_b,
                       reinterpret_cast<char*>(e->in_len.p) + b0 * len_b, reinterpret_cast<char*>(e->tgt_len.p) + b0 * len_b,
                       reinterpret_cast<char*>(e->losses.p) + b0 * es, dg, 1.0, reinterpret_cast<char*>(e->ws.p) + ws_off[k], sc);
     if (rc != E2E_OK) { cudaDeviceSynchronize(); return rc; }
     E2E_CUDA_TRY(cudaEventRecord(e->ev_comp[k], sc));
     E2E_CUDA_TRY(cudaStreamWaitEvent(e->s_out, e->ev_comp[k], 0));
+    if (trace) cudaEventRecord(tr[4 * k + 2], sc);
     E2E_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(grads) + b0 * row_b, dg, nb * row_b, cudaMemcpyDeviceToHost, e->s_out));
     E2E_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(losses) + b0 * es, reinterpret_cast<char*>(e->losses.p) + b0 * es, nb * es,
                                  cudaMemcpyDeviceToHost, e->s_out));
+    if (trace) { cudaEventRecord(tr[4 * k + 3], e->s_out); host_us[k] = now_us() - host_t0; }
   }
   E2E_CUDA_TRY(cudaStreamSynchronize(e->s_out));
+  if (trace) {
+    const double host_done = now_us() - host_t0;
+    fprintf(stderr, "[e2e host trace] %d chunks; host: ", nch);
+    for (int k = 0; k < nch; k++) fprintf(stderr, "issued[%d] %.0f us  ", k, host_us[k]);
+    fprintf(stderr, "synced %.0f us\n", host_done);
+    for (int k = 0; k < nch; k++) {
+      float a = 0, b = 0, c = 0, dd = 0;
+      cudaEventElapsedTime(&a, tr[4 * nch], tr[4 * k]); cudaEventElapsedTime(&b, tr[4 * nch], tr[4 * k + 1]);
+      cudaEventElapsedTime(&c, tr[4 * nch], tr[4 * k + 2]); cudaEventElapsedTime(&dd, tr[4 * nch], tr[4 * k + 3]);
+      fprintf(stderr, "  chunk %d (%d utt): copy-in done %.0f us, kernels %.0f -> %.0f us, copy-out done %.0f us\n", k, cd[k].batch,
+              a * 1e3, b * 1e3, c * 1e3, dd * 1e3);
+    }
+    for (cudaEvent_t& ev : tr) cudaEventDestroy(ev);
+  }
   return E2E_OK;
 }
 

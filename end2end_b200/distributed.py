@@ -93,13 +93,14 @@ class LossComm:
         L = _lib.load()
         rank, world = dist.get_rank(), dist.get_world_size()
         buf = ctypes.create_string_buffer(128)
-        ok = 1
-        if rank == 0 and L.e2e_ctc_comm_unique_id(buf) != 0:
-            ok = 0
-        box = [bytes(buf.raw) if ok else None]
-        dist.broadcast_object_list(box, src=0)          # every rank learns the id (or that rank 0 has no libnccl)
-        if box[0] is None:
+        # EVERY rank checks that it can resolve libnccl before anyone enters the collective ncclCommInitRank: a rank
+        # that returned early from e2e_ctc_comm_create would leave the others blocked inside it forever
+        have = torch.tensor([1 if L.e2e_ctc_comm_unique_id(buf) == 0 else 0], device="cuda")
+        dist.all_reduce(have, op=dist.ReduceOp.MIN)
+        if int(have.item()) == 0:
             return None
+        box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=0)          # every rank takes rank 0's id
         h = ctypes.c_void_p()
         rc = L.e2e_ctc_comm_create(box[0], world, rank, ctypes.byref(h))
         flag = torch.tensor([1 if rc == 0 else 0], device="cuda")
@@ -127,6 +128,7 @@ class _ShardedLossFunction(Function):
         known = float(global_batch) if global_batch is not None else None
         ctx.folded = 1.0 / known if (mean and known) else 1.0     # constant part of grad_output baked into the kernel
         ctx.on_device = logits.is_cuda
+        ctx.redo, ctx.pristine = None, True
         reducing = group is not False and dist.is_available() and dist.is_initialized()
         if logits.is_cuda and need_grad and (known or not mean):
             # fast path (the global batch is known, or the loss is a plain sum): the reduce kernel already
@@ -134,6 +136,7 @@ class _ShardedLossFunction(Function):
             # all-reduce buffer and the result -- no host-side arithmetic around the collective
             _, ctx.grads, total, _ = engine.step(logits, targets, logits_lengths, targets_lengths, from_logits,
                                                  grad_scale=ctx.folded, reduce_scale=ctx.folded)
+            ctx.redo = (logits, targets, logits_lengths, targets_lengths, from_logits)
             if reducing:                                                    # THE collective of this path
                 comm = LossComm.get() if group is None else None
                 if comm is not None:
@@ -145,6 +148,7 @@ class _ShardedLossFunction(Function):
         if logits.is_cuda and need_grad:
             _, ctx.grads, _, pair = engine.step(logits, targets, logits_lengths, targets_lengths, from_logits,
                                                 grad_scale=ctx.folded, want_pair=True)
+            ctx.redo = (logits, targets, logits_lengths, targets_lengths, from_logits)
         elif logits.is_cuda:
             losses, _ = engine.forward(logits, targets, logits_lengths, targets_lengths, from_logits)
             ctx.grads = None
@@ -169,6 +173,10 @@ class _ShardedLossFunction(Function):
         if ctx.mean and not isinstance(ctx.inv_n, float):
             g = g * ctx.inv_n.to(g.dtype)              # global count only known after the all-reduce
         if ctx.on_device:
+            if not ctx.pristine and ctx.redo is not None:
+                # a second backward through a retained graph: the block was scaled in place by the first one; rebuild it
+                _, ctx.grads, _, _ = ctx.engine.step(*ctx.redo[:4], ctx.redo[4], grad_scale=ctx.folded)
+            ctx.pristine = False
             grad = ctx.engine.scale_rows_(ctx.grads, g)
         else:
             grad = ctx.grads * (g.to(ctx.grads.device).reshape(1, 1, 1) * ctx.folded)
@@ -194,6 +202,20 @@ class ShardedCTCLoss(nn.Module):
         self._group, self._global_batch = process_group, global_batch
         self._engine = engine if engine is not None else CTCLossEngine(blank_idx)
 
+    def graphed(self, logits, targets, logits_lengths, targets_lengths):
+        """The sharded step for device tensors at fixed addresses as CUDA graphs (SURVEY 8(f1) + 8(e)); needs
+        ``reduce=True`` and, for a mean, ``global_batch``.  See :class:`ShardedGraphedStep`."""
+        if not self._reduce:
+            raise ValueError("graphed(): reduce=True required (nothing is exchanged otherwise: use CTCLoss.graphed)")
+        mean = bool(self._size_average)
+        if mean and self._global_batch is None:
+            raise ValueError("graphed(): a mean over the ranks needs global_batch")
+        if self._time_major:
+            logits = logits.permute(1, 0, 2)
+        scale = 1.0 / float(self._global_batch) if mean else 1.0
+        return ShardedGraphedStep(self._engine, logits, targets, logits_lengths, targets_lengths,
+                                  not self._after_logsoftmax, scale, self._group, self._time_major)
+
     def forward(self, logits, targets, logits_lengths, targets_lengths):
         if self._time_major:
             logits = logits.permute(1, 0, 2)
@@ -204,3 +226,56 @@ class ShardedCTCLoss(nn.Module):
         return _ShardedLossFunction.apply(self._engine, logits, targets, logits_lengths, targets_lengths,
                                           not self._after_logsoftmax, bool(self._size_average),
                                           self._group, self._global_batch)
+
+
+class ShardedGraphedStep:
+    """The sharded training step of the loss, replayed as CUDA graphs, with the ONE collective of the path off the
+    critical path: ``replay()`` launches the rank's captured step (memset, lattice kernel, reduction) on the current
+    stream and enqueues the all-reduce of its scalar on a SIDE stream, so the collective of step k overlaps the
+    lattice kernel of step k+1 -- the gradient never depends on it (the global batch size is folded in).  Two
+    captured steps with their own scalar buffers alternate, so step k+1's reduction never overwrites the buffer
+    step k's all-reduce is still reading; ``replay()`` makes the current stream wait only for the all-reduce of step
+    k-2.  ``wait()`` joins the side stream; ``total`` then holds the global loss of the last replay."""
+
+    def __init__(self, engine, logits, targets, logits_lengths, targets_lengths, from_logits, scale, group, time_major):
+        a = engine.graphed_step(logits, targets, logits_lengths, targets_lengths, from_logits, grad_scale=scale, reduce_scale=scale)
+        b = engine.graphed_step(logits, targets, logits_lengths, targets_lengths, from_logits, grad_scale=scale, reduce_scale=scale, share=a)
+        self._steps = (a, b)
+        self._k = 0
+        self._group = group
+        self._reducing = group is not False and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self._comm = LossComm.get() if (self._reducing and group is None) else None
+        self._side = torch.cuda.Stream(device=logits.device)
+        self._ev_step = [torch.cuda.Event(), torch.cuda.Event()]
+        self._ev_red = [None, None]
+        self.grad = a.grads.permute(1, 0, 2) if time_major else a.grads
+        self.total = a.reduced
+
+    def replay(self):
+        i = self._k & 1
+        self._k += 1
+        step = self._steps[i]
+        cur = torch.cuda.current_stream(step.device)
+        if self._ev_red[i] is not None:
+            cur.wait_event(self._ev_red[i])          # the all-reduce that last used this scalar buffer (two steps ago)
+        step.launch()
+        self.total = step.reduced
+        if self._reducing:
+            self._ev_step[i].record(cur)
+            self._side.wait_event(self._ev_step[i])
+            with torch.cuda.stream(self._side):
+                if self._comm is not None:
+                    self._comm.allreduce_sum_(step.reduced)
+                else:
+                    dist.all_reduce(step.reduced, op=dist.ReduceOp.SUM, group=self._group)
+                ev = torch.cuda.Event()
+                ev.record(self._side)
+            self._ev_red[i] = ev
+        return self.total, self.grad
+
+    def wait(self):
+        """Make the current stream wait for the outstanding all-reduces (call before reading ``total``)."""
+        for ev in self._ev_red:
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+        return self.total

@@ -242,6 +242,27 @@ class CTCLossEngine:
                 float(reduce_scale if reduce_scale is not None else 1.0), _ptr(ws), ws.numel(), _stream(dev)))
         return losses, grads, reduced, pair
 
+    def graphed_step(self, logits, targets, logits_lengths, targets_lengths, from_logits=False, grad_scale=1.0,
+                     reduce_scale=None, want_pair=False, comm=None, share=None):
+        """The same step as :meth:`step`, captured ONCE into a CUDA graph bound to these tensors
+        (SURVEY 8(f1)): ``g = engine.graphed_step(...)`` runs the step and returns a :class:`GraphedStep`;
+        every ``g.launch()`` replays it with one driver call.  The tensors (and the outputs ``g.losses``,
+        ``g.grads``, ``g.reduced``, ``g.pair``) keep their addresses; a training loop copies each batch into
+        them.  ``comm``: a library communicator handle (``distributed.LossComm``) whose scalar all-reduce of
+        ``reduced`` becomes part of the graph.  ``share``: another GraphedStep over the SAME input tensors whose
+        ``losses`` / ``grads`` / workspace this one reuses (only ``reduced`` / ``pair`` are its own): two such
+        steps replayed alternately let a side-stream all-reduce of step k's scalar overlap step k+1."""
+        _require_cuda()
+        logits = logits.detach()
+        dev = logits.device
+        if not (targets.is_cuda and logits_lengths.is_cuda and targets_lengths.is_cuda):
+            raise ValueError("graphed_step needs device-resident targets and lengths (the graph is bound to their addresses)")
+        with _on_device(dev):
+            pb = _Problem(self.blank_idx, logits, targets, logits_lengths, targets_lengths, from_logits, dev)
+            if pb.logits is not logits:
+                raise ValueError("graphed_step needs logits with a unit alphabet stride (no hidden copy: the graph reads this tensor)")
+            return GraphedStep(self, pb, float(grad_scale), reduce_scale, want_pair, comm, share)
+
     def scale_rows_(self, grads, grad_output):
         """``grads[b] *= grad_output[b or 0]`` in place (functions/forward_backward.py:34); utterances whose
         factor is exactly 1 are skipped on the device."""
@@ -400,6 +421,46 @@ class CTCLossEngine:
         """(h2d_bytes, d2h_bytes) of the last host-tensor call."""
         h = self._host.get(torch.cuda.current_device())
         return h.traffic() if h else (0, 0)
+
+
+class GraphedStep:
+    """One captured training step of the loss (``e2e_ctc_graph_*`` in include/e2e_ctc.h)."""
+
+    def __init__(self, engine, pb, grad_scale, reduce_scale, want_pair, comm, share=None):
+        self._L = engine._L
+        self._pb = pb                       # keeps the input tensors alive
+        dev = pb.logits.device
+        self.device = dev
+        self.losses = share.losses if share is not None else torch.empty(pb.B, dtype=pb.logits.dtype, device=dev)
+        self.grads = share.grads if share is not None else pb.new_grads()
+        self.reduced = torch.empty((), dtype=pb.logits.dtype, device=dev) if reduce_scale is not None else None
+        self.pair = torch.empty(2, dtype=torch.float64, device=dev) if want_pair else None
+        # its own workspace (graphs of several batches coexist), unless it alternates with `share` on one stream
+        self._ws = share._ws if share is not None else torch.empty(engine._ws_need(pb), dtype=torch.uint8, device=dev)
+        self._comm = comm
+        self.handle = ctypes.c_void_p(0)
+        _lib.check(self._L.e2e_ctc_graph_create(
+            ctypes.byref(pb.desc), _ptr(pb.logits), _ptr(pb.targets), _ptr(pb.logits_lengths), _ptr(pb.targets_lengths),
+            _ptr(self.losses), _ptr(self.grads), grad_scale, _ptr(self.reduced), _ptr(self.pair),
+            float(reduce_scale if reduce_scale is not None else 1.0), _ptr(self._ws), self._ws.numel(),
+            comm if comm is not None else ctypes.c_void_p(0), ctypes.byref(self.handle)))
+        self._launch = self._L.e2e_ctc_graph_launch
+        self._dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+
+    def launch(self):
+        """Enqueue one replay on the current stream; results land in ``losses`` / ``grads`` / ``reduced``."""
+        rc = self._launch(self.handle, _raw_stream(self._dev_index))
+        if rc:
+            _lib.check(rc)
+        return self
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self._L.e2e_ctc_graph_destroy(self.handle)
+                self.handle = ctypes.c_void_p(0)
+        except Exception:
+            pass
 
 
 class _HostEngine:

@@ -46,6 +46,39 @@ class ForwardBackwardLossBase(nn.Module):
         return ForwardBackwardLossFunction.apply(self._engine, logits, targets, logits_lengths,
                                                  targets_lengths, not self._after_logsoftmax, reduction)
 
+    def graphed(self, logits, targets, logits_lengths, targets_lengths):
+        """the whole step of this criterion (``forward`` + the ``backward`` of ``loss.sum()``) for
+        device tensors at FIXED addresses, captured once; see :class:`GraphedCTCStep`.  A training loop whose
+        batches are copied into the same buffers then pays one driver call per step instead of the Python
+        autograd round trip (reference: modules/ctc_loss.py:37-57 + functions/forward_backward.py:6-35)."""
+        if self._time_major:
+            logits = logits.permute(1, 0, 2)
+        B = logits.size(0)
+        mean = bool(self._reduce and self._size_average)
+        scale = 1.0 / B if mean else 1.0
+        step = self._engine.graphed_step(logits, targets, logits_lengths, targets_lengths,
+                                         from_logits=not self._after_logsoftmax, grad_scale=scale,
+                                         reduce_scale=scale if self._reduce else None)
+        return GraphedCTCStep(step, self._time_major, bool(self._reduce))
+
+
+class GraphedCTCStep:
+    """Forward + backward of a criterion captured into one CUDA graph (``criterion.graphed(...)``).
+
+    ``replay()`` enqueues the step on the current stream and returns ``(loss, grad)``: the loss the module's
+    ``forward`` would return (per-utterance ``[B]``, or the 0-dim sum / mean) and ``d loss.sum() / d logits`` in
+    the layout of ``logits`` -- what ``loss.backward()`` leaves in ``logits.grad`` for an upstream gradient of one.
+    Both are views of buffers owned by the step: they are overwritten by the next ``replay()``."""
+
+    def __init__(self, step, time_major, reduced):
+        self._step = step
+        self.loss = step.reduced if reduced else step.losses
+        self.grad = step.grads.permute(1, 0, 2) if time_major else step.grads
+
+    def replay(self):
+        self._step.launch()
+        return self.loss, self.grad
+
 
 class CTCLoss(ForwardBackwardLossBase):
     """

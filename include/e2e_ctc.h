@@ -170,6 +170,22 @@ int e2e_ctc_comm_create(const void* id128, int32_t nranks, int32_t rank, e2e_ctc
 void e2e_ctc_comm_destroy(e2e_ctc_comm* comm);
 int e2e_ctc_comm_allreduce_sum(e2e_ctc_comm* comm, void* buf, int64_t count, int32_t dtype, void* cuda_stream);
 
+/* ------------------------------------------------------------------- CUDA-graph step -------- */
+
+/* The training step of e2e_ctc_loss_step_device -- and, when `comm` is non-NULL, the in-place all-reduce of
+ * `reduced` -- captured once into a CUDA graph bound to these buffers (the reference's step is
+ * modules/ctc_loss.py:37-57 + functions/forward_backward.py:6-35; here it replays with ONE driver call).
+ * The buffers and the workspace must stay alive and at the same addresses for the lifetime of the graph; their
+ * CONTENTS may change between launches (a training loop copies each batch into the same buffers).
+ * e2e_ctc_graph_create runs the step once (results are valid afterwards) and synchronises; launch only enqueues. */
+typedef struct e2e_ctc_graph e2e_ctc_graph;
+int e2e_ctc_graph_create(const e2e_ctc_desc* desc, const void* logits, const void* targets,
+                         const void* logits_lengths, const void* targets_lengths, void* losses, void* grads,
+                         double grad_scale, void* reduced, double* reduced_f64, double reduce_scale,
+                         void* workspace, size_t workspace_bytes, e2e_ctc_comm* comm, e2e_ctc_graph** out);
+int e2e_ctc_graph_launch(e2e_ctc_graph* graph, void* cuda_stream);
+void e2e_ctc_graph_destroy(e2e_ctc_graph* graph);
+
 /* --------------------------------------------------------------- greedy decode, device ----- */
 
 size_t e2e_ctc_greedy_workspace_bytes(const e2e_ctc_desc* desc);

@@ -711,6 +711,64 @@ def test_c_abi_direct_calls(e2e):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("cfg,B,time_major,reduce,mean", [("c1", 4, False, True, True), ("c2", 16, True, True, False),
+                                                          ("c4", 6, False, False, False), ("c3", 64, False, True, True)])
+def test_graphed_step_matches_autograd_and_oracle(e2e, cfg, B, time_major, reduce, mean):
+    """criterion.graphed(...) captures forward + backward once (e2e_ctc_graph_*); every replay must
+    give what the autograd path gives -- bitwise, it runs the same kernels -- and the oracle's result, also after
+    the CONTENTS of the bound buffers changed (a training loop copies each batch into them)."""
+    from end2end_b200 import _lib
+    _, T_, V, Lmin, Lmax, seed, dtype, full = oracle.CONFIGS[cfg]
+    crit = e2e.CTCLoss(reduce=reduce, size_average=mean, time_major=time_major)
+    x, tg, ll, tl = oracle.make_inputs(B, T_, V, Lmin, Lmax, seed, dtype=dtype, full_length=full)
+    buf = (x.permute(1, 0, 2).contiguous() if time_major else x).cuda()
+    tgc, llc, tlc = cuda(tg, ll, tl)
+    step = crit.graphed(buf, tgc, llc, tlc)
+    for rnd in range(3):
+        if rnd:      # a new batch into the SAME buffers
+            x, tg, ll, tl = oracle.make_inputs(B, T_, V, Lmin, Lmax, seed + rnd, dtype=dtype, full_length=full)
+            buf.copy_(x.permute(1, 0, 2) if time_major else x)
+            tgc.copy_(tg); llc.copy_(ll); tlc.copy_(tl)
+        before = _lib.launch_count()
+        loss, grad = step.replay()
+        assert _lib.launch_count() - before >= 1       # the graph's kernels are counted at launch
+        leaf = buf.detach().clone().requires_grad_()
+        ref = crit(leaf, tgc, llc, tlc)
+        ref.sum().backward()
+        assert torch.equal(loss, ref.detach()) and torch.equal(grad, leaf.grad), (cfg, rnd)
+        xo = x.float().clone().requires_grad_()
+        lo = oracle.ctc_loss_module(oracle.engine(0), xo, tg, ll, tl, reduce=reduce, size_average=mean)
+        lo.sum().backward()
+        go = xo.grad.permute(1, 0, 2) if time_major else xo.grad
+        if dtype == torch.bfloat16:
+            assert_parity(loss.float(), lo.detach(), rtol=BF16_RTOL, what=cfg + " graphed loss")
+            assert_parity(grad.float(), go, rtol=BF16_RTOL, what=cfg + " graphed grad")
+        else:
+            assert_parity(loss, lo.detach(), what=cfg + " graphed loss")
+            assert_parity(grad, go, what=cfg + " graphed grad")
+    with pytest.raises(ValueError):
+        crit.graphed(buf, tg, llc, tlc)                # host-resident targets cannot be bound into a graph
+
+
+def test_sharded_graphed_step_single_rank(e2e):
+    """ShardedCTCLoss.graphed on one rank (no process group): two alternating captured steps, same results as the
+    module; the collective path is covered by tests/dist_check.py under torchrun."""
+    from end2end_b200.distributed import ShardedCTCLoss
+    x, tg, ll, tl = oracle.make_inputs(12, 90, 29, 5, 30, 5)
+    xc, tgc, llc, tlc = cuda(x, tg, ll, tl)
+    crit = ShardedCTCLoss(reduce=True, size_average=True, global_batch=24)
+    step = crit.graphed(xc, tgc, llc, tlc)
+    leaf = xc.clone().requires_grad_()
+    ref = crit(leaf, tgc, llc, tlc)
+    ref.backward()
+    for _ in range(3):
+        total, grad = step.replay()
+        step.wait()
+        assert torch.equal(total, ref.detach()) and torch.equal(grad, leaf.grad)
+    with pytest.raises(ValueError):
+        ShardedCTCLoss(reduce=True, size_average=True).graphed(xc, tgc, llc, tlc)     # a mean needs global_batch
+
+
 def test_host_engine_traffic_and_pinned_buffers(e2e):
     x, tg, ll, tl = oracle.make_inputs(8, 60, 29, 5, 20, 17)
     eng = e2e.CTCLossEngine(0)
