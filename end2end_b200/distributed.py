@@ -202,7 +202,7 @@ class ShardedCTCLoss(nn.Module):
         self._group, self._global_batch = process_group, global_batch
         self._engine = engine if engine is not None else CTCLossEngine(blank_idx)
 
-    def graphed(self, logits, targets, logits_lengths, targets_lengths):
+    def graphed(self, logits, targets, logits_lengths, targets_lengths, workspace=None):
         """The sharded step for device tensors at fixed addresses as CUDA graphs (SURVEY 8(f1) + 8(e)); needs
         ``reduce=True`` and, for a mean, ``global_batch``.  See :class:`ShardedGraphedStep`."""
         if not self._reduce:
@@ -214,7 +214,7 @@ class ShardedCTCLoss(nn.Module):
             logits = logits.permute(1, 0, 2)
         scale = 1.0 / float(self._global_batch) if mean else 1.0
         return ShardedGraphedStep(self._engine, logits, targets, logits_lengths, targets_lengths,
-                                  not self._after_logsoftmax, scale, self._group, self._time_major)
+                                  not self._after_logsoftmax, scale, self._group, self._time_major, workspace)
 
     def forward(self, logits, targets, logits_lengths, targets_lengths):
         if self._time_major:
@@ -237,15 +237,23 @@ class ShardedGraphedStep:
     step k's all-reduce is still reading; ``replay()`` makes the current stream wait only for the all-reduce of step
     k-2.  ``wait()`` joins the side stream; ``total`` then holds the global loss of the last replay."""
 
-    def __init__(self, engine, logits, targets, logits_lengths, targets_lengths, from_logits, scale, group, time_major):
-        a = engine.graphed_step(logits, targets, logits_lengths, targets_lengths, from_logits, grad_scale=scale, reduce_scale=scale)
+    _side_streams = {}     # ONE side stream per device for every step's all-reduce: NCCL operations of a communicator are
+                   # issued in the same order on every rank, and that order is the replay order
+
+    def __init__(self, engine, logits, targets, logits_lengths, targets_lengths, from_logits, scale, group, time_major,
+                 workspace=None):
+        a = engine.graphed_step(logits, targets, logits_lengths, targets_lengths, from_logits, grad_scale=scale, reduce_scale=scale,
+                                workspace=workspace)
         b = engine.graphed_step(logits, targets, logits_lengths, targets_lengths, from_logits, grad_scale=scale, reduce_scale=scale, share=a)
         self._steps = (a, b)
         self._k = 0
         self._group = group
         self._reducing = group is not False and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self._comm = LossComm.get() if (self._reducing and group is None) else None
-        self._side = torch.cuda.Stream(device=logits.device)
+        key = logits.device.index if logits.device.index is not None else torch.cuda.current_device()
+        if key not in ShardedGraphedStep._side_streams:
+            ShardedGraphedStep._side_streams[key] = torch.cuda.Stream(device=logits.device)
+        self._side = ShardedGraphedStep._side_streams[key]
         self._ev_step = [torch.cuda.Event(), torch.cuda.Event()]
         self._ev_red = [None, None]
         self.grad = a.grads.permute(1, 0, 2) if time_major else a.grads

@@ -243,7 +243,7 @@ class CTCLossEngine:
         return losses, grads, reduced, pair
 
     def graphed_step(self, logits, targets, logits_lengths, targets_lengths, from_logits=False, grad_scale=1.0,
-                     reduce_scale=None, want_pair=False, comm=None, share=None):
+                     reduce_scale=None, want_pair=False, comm=None, share=None, workspace=None):
         """The same step as :meth:`step`, captured ONCE into a CUDA graph bound to these tensors
         (SURVEY 8(f1)): ``g = engine.graphed_step(...)`` runs the step and returns a :class:`GraphedStep`;
         every ``g.launch()`` replays it with one driver call.  The tensors (and the outputs ``g.losses``,
@@ -251,7 +251,9 @@ class CTCLossEngine:
         them.  ``comm``: a library communicator handle (``distributed.LossComm``) whose scalar all-reduce of
         ``reduced`` becomes part of the graph.  ``share``: another GraphedStep over the SAME input tensors whose
         ``losses`` / ``grads`` / workspace this one reuses (only ``reduced`` / ``pair`` are its own): two such
-        steps replayed alternately let a side-stream all-reduce of step k's scalar overlap step k+1."""
+        steps replayed alternately let a side-stream all-reduce of step k's scalar overlap step k+1.
+        ``workspace``: a uint8 CUDA tensor of at least :meth:`workspace_bytes` bytes to use as scratch -- graphs
+        that are only ever replayed one after another on ONE stream may share one (each otherwise owns its own)."""
         _require_cuda()
         logits = logits.detach()
         dev = logits.device
@@ -261,7 +263,12 @@ class CTCLossEngine:
             pb = _Problem(self.blank_idx, logits, targets, logits_lengths, targets_lengths, from_logits, dev)
             if pb.logits is not logits:
                 raise ValueError("graphed_step needs logits with a unit alphabet stride (no hidden copy: the graph reads this tensor)")
-            return GraphedStep(self, pb, float(grad_scale), reduce_scale, want_pair, comm, share)
+            return GraphedStep(self, pb, float(grad_scale), reduce_scale, want_pair, comm, share, workspace)
+
+    def workspace_bytes(self, logits, targets, logits_lengths, targets_lengths, from_logits=False):
+        """Scratch bytes one step over tensors of these shapes needs (``e2e_ctc_loss_workspace_bytes``)."""
+        pb = _Problem.make(self.blank_idx, logits.detach(), targets, logits_lengths, targets_lengths, from_logits, logits.device)
+        return self._ws_need(pb)
 
     def scale_rows_(self, grads, grad_output):
         """``grads[b] *= grad_output[b or 0]`` in place (functions/forward_backward.py:34); utterances whose
@@ -426,7 +433,7 @@ class CTCLossEngine:
 class GraphedStep:
     """One captured training step of the loss (``e2e_ctc_graph_*`` in include/e2e_ctc.h)."""
 
-    def __init__(self, engine, pb, grad_scale, reduce_scale, want_pair, comm, share=None):
+    def __init__(self, engine, pb, grad_scale, reduce_scale, want_pair, comm, share=None, workspace=None):
         self._L = engine._L
         self._pb = pb                       # keeps the input tensors alive
         dev = pb.logits.device
@@ -436,7 +443,12 @@ class GraphedStep:
         self.reduced = torch.empty((), dtype=pb.logits.dtype, device=dev) if reduce_scale is not None else None
         self.pair = torch.empty(2, dtype=torch.float64, device=dev) if want_pair else None
         # its own workspace (graphs of several batches coexist), unless it alternates with `share` on one stream
-        self._ws = share._ws if share is not None else torch.empty(engine._ws_need(pb), dtype=torch.uint8, device=dev)
+        need = engine._ws_need(pb)
+        if share is not None:
+            workspace = share._ws
+        if workspace is not None and (workspace.device != dev or workspace.dtype != torch.uint8 or workspace.numel() < need):
+            raise ValueError("graphed_step: workspace must be a uint8 tensor of >= %d bytes on %s" % (need, dev))
+        self._ws = workspace if workspace is not None else torch.empty(need, dtype=torch.uint8, device=dev)
         self._comm = comm
         self.handle = ctypes.c_void_p(0)
         _lib.check(self._L.e2e_ctc_graph_create(

@@ -46,7 +46,7 @@ class ForwardBackwardLossBase(nn.Module):
         return ForwardBackwardLossFunction.apply(self._engine, logits, targets, logits_lengths,
                                                  targets_lengths, not self._after_logsoftmax, reduction)
 
-    def graphed(self, logits, targets, logits_lengths, targets_lengths):
+    def graphed(self, logits, targets, logits_lengths, targets_lengths, workspace=None):
         """the whole step of this criterion (``forward`` + the ``backward`` of ``loss.sum()``) for
         device tensors at FIXED addresses, captured once; see :class:`GraphedCTCStep`.  A training loop whose
         batches are copied into the same buffers then pays one driver call per step instead of the Python
@@ -58,7 +58,7 @@ class ForwardBackwardLossBase(nn.Module):
         scale = 1.0 / B if mean else 1.0
         step = self._engine.graphed_step(logits, targets, logits_lengths, targets_lengths,
                                          from_logits=not self._after_logsoftmax, grad_scale=scale,
-                                         reduce_scale=scale if self._reduce else None)
+                                         reduce_scale=scale if self._reduce else None, workspace=workspace)
         return GraphedCTCStep(step, self._time_major, bool(self._reduce))
 
 

@@ -221,7 +221,9 @@ int e2e_ctc_engine_greedy_host(e2e_ctc_engine* engine, const e2e_ctc_desc* desc,
                                const void* logits_lengths, int64_t* decoded,
                                int64_t* decoded_lengths);
 
-/* Bytes moved by the last engine call (for benchmarks): host->device and device->host. */
+/* Bytes moved by the last engine call (for benchmarks): host->device and device->host.  Every byte that crosses
+ * PCIe is counted, whether the copy engine moved it or -- result buffers in pinned host memory -- the kernels
+ * stored it into the caller's buffer directly. */
 int e2e_ctc_engine_last_traffic(const e2e_ctc_engine* engine, uint64_t* h2d_bytes,
                                 uint64_t* d2h_bytes);
 

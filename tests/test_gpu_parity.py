@@ -820,6 +820,32 @@ def test_host_engine_chunked_pipeline(e2e, chunks):
         eng.compute(x, torch.full_like(tg, 11), ll, tl, from_logits=True)
 
 
+@pytest.mark.parametrize("cfg,B", [("c1", 4), ("c2", 12), ("c4", 5), ("c3", 40)])
+def test_host_engine_zero_copy_results_equal_staged(e2e, cfg, B):
+    """Pinned result buffers are written by the kernels directly (no device->host copy stage); pageable or
+    E2E_CTC_HOST_ZERO_COPY=0 takes the staged copies.  Same bits either way, single-stream and chunked."""
+    _, T_, V, Lmin, Lmax, seed, dtype, full = oracle.CONFIGS[cfg]
+    x, tg, ll, tl = oracle.make_inputs(B, T_, V, Lmin, Lmax, seed, dtype=dtype, full_length=full)
+    eng = e2e.CTCLossEngine(0)
+    pinned = [t.pin_memory() for t in (x, tg, ll, tl)]
+    outs = []
+    for env in ({"E2E_CTC_HOST_ZERO_COPY": "0", "E2E_CTC_HOST_CHUNKS": "1"}, {"E2E_CTC_HOST_CHUNKS": "1"},
+                {"E2E_CTC_HOST_CHUNKS": "3"}, {"E2E_CTC_HOST_ZERO_COPY": "0", "E2E_CTC_HOST_CHUNKS": "3"}, {}):
+        outs.append(_with_env(env, lambda: eng.compute(*pinned, from_logits=True)))
+        outs.append(_with_env(env, lambda: eng.compute(pinned[0], tg, ll, tl, from_logits=True)))   # pageable index tensors
+    for l_, g_ in outs[1:]:
+        assert torch.equal(l_, outs[0][0]) and torch.equal(g_, outs[0][1])
+    h2d, d2h = eng.last_host_traffic()
+    assert d2h == x.numel() * x.element_size() + B * x.element_size()       # result bytes are counted either way
+    l_ref, g_ref = _oracle_sub_batched(x, tg, ll, tl, 64)
+    g_ref = _logits_grad_ref(g_ref, l_ref, ll)
+    if dtype == torch.bfloat16:
+        assert_parity(outs[0][1].float(), g_ref, rtol=BF16_RTOL, what=cfg + " host grads")
+    else:
+        assert_parity(outs[0][0], l_ref, what=cfg + " host losses")
+        assert_parity(outs[0][1], g_ref, what=cfg + " host grads")
+
+
 def test_fuzz_every_kernel_vs_oracle(e2e):
     """Random shapes, dtypes, strides, blanks, emission scales, tight alignments and infeasible rows, each on a
     randomly forced lattice kernel (or the library's own dispatch), fused and split: losses, gradients and

@@ -62,3 +62,32 @@ xc, tgc, llc, tlc = x.cuda(), tg.cuda(), ll.cuda(), tl.cuda()
 print("device step (engine.step): %.1f us" % timeit(lambda: eng.step(xc, tgc, llc, tlc, True, 1.0 / B, 1.0 / B), n=100))
 g = eng.graphed_step(xc, tgc, llc, tlc, True, 1.0 / B, 1.0 / B)
 print("device step (graph replay): %.1f us" % timeit(lambda: g.launch(), n=200))
+# 5. where the Python wrapper's time goes (the pieces of CTCLossEngine._compute_host, timed separately)
+import ctypes
+from end2end_b200 import _lib
+from end2end_b200.engine import _Problem, _ptr
+cpu = torch.device("cpu")
+
+
+def t_us(fn, n=200):
+    fn()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        fn()
+    return (time.perf_counter() - t0) / n * 1e6
+
+
+print("_Problem(...) host: %.1f us" % t_us(lambda: _Problem(0, xp, tg, ll, tl, True, cpu, validate=False)))
+print("torch.empty(B, pinned): %.1f us" % t_us(lambda: torch.empty(B, dtype=xp.dtype, pin_memory=True)))
+print("torch.empty_strided(logits, pinned): %.1f us" % t_us(lambda: torch.empty_strided(xp.size(), xp.stride(), dtype=xp.dtype, pin_memory=True)))
+keep = []
+print("  ... while the previous one is still alive: %.1f us" % t_us(lambda: (keep.append(torch.empty_strided(xp.size(), xp.stride(), dtype=xp.dtype, pin_memory=True)), len(keep) > 1 and keep.pop(0))))
+pb = _Problem(0, xp, tg, ll, tl, True, cpu, validate=False)
+losses = torch.empty(B, dtype=xp.dtype, pin_memory=True)
+grads = torch.empty_strided(xp.size(), xp.stride(), dtype=xp.dtype, pin_memory=True)
+h = eng._host_engine(torch.cuda.current_device())
+L = _lib.load()
+for chunks in ("1", "2", "3", "4", "6", "8"):
+    os.environ["E2E_CTC_HOST_CHUNKS"] = chunks
+    print("C call only, chunks %s: %.1f us" % (chunks, t_us(lambda: L.e2e_ctc_engine_loss_host(
+        h.handle, ctypes.byref(pb.desc), _ptr(pb.logits), _ptr(pb.targets), _ptr(pb.logits_lengths), _ptr(pb.targets_lengths), _ptr(losses), _ptr(grads)), n=60)))
