@@ -252,6 +252,9 @@ static bool make_fused_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   // CTA is laid out for the shortest per-frame chain; otherwise several CTAs share an SM and the layout is
   // sized for occupancy
   bool latency = 2 * d.batch <= 148;
+  // gather mode (K1 and K3 do the streaming): the kernel is a latency chain per CTA even with two CTAs on an SM --
+  // the eight-warp layout (four combiners) measured 9 % faster than the occupancy layout on BASELINE config 4
+  if (!dense && 2 * d.batch <= 2 * 148) latency = true;
   if (tn.latency == 0 || tn.latency == 1) latency = tn.latency == 1;
   FzLayout L;
   memset(&L, 0, sizeof(L));
@@ -281,7 +284,9 @@ static bool make_fused_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   L.PB = 8;            // frames per producer block (one warp per frame, four frames in flight)
   L.pb_log2 = 3;
   L.R = 2 * L.PB;                                 // at least two producer blocks in the ring, four when they fit 32 KB
-  if ((size_t)4 * L.PB * L.es * 8 <= 32 * 1024) L.R = 4 * L.PB;
+  // gather mode: four blocks -- a producer's block is two dependent L2 round trips (~4k cycles), twice what the sweep
+  // needs for a block, so with two blocks in the ring the lattice warp waited for emissions 45 % of its time (measured)
+  if ((size_t)4 * L.PB * L.es * 8 <= 32 * 1024 || !dense) L.R = 4 * L.PB;
   while (L.R < 128 && (size_t)2 * L.R * L.es * 8 <= (size_t)(latency ? 48 : 24) * 1024) L.R *= 2;
   if (tn.r >= 2 * L.PB && !(tn.r & (tn.r - 1))) L.R = tn.r;
   if (L.R > 16 * L.PB) L.R = 16 * L.PB;   // at most 16 emission blocks (one mbarrier each)
@@ -332,6 +337,8 @@ static bool make_fused_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   p->off_stats = o; o += dense ? 0 : align256(rows * (d.dtype == E2E_F64 ? 16 : 8));
   p->off_stash = o; o += align256(rows * p->roww * 4);
   p->off_post = o; o += dense ? 0 : align256(rows * p->post_stride * 4);
+  p->emis_stride = dense ? 0 : Lmax + 1;         // [label 0 .. label Lmax-1 | blank] doubles per frame, written by K1
+  p->off_emis = o; o += dense ? 0 : align256(rows * (size_t)p->emis_stride * 8);
   p->total = o;
   return true;
 }
@@ -369,7 +376,9 @@ static int check_ws(const void* ws, size_t have, size_t need) {
 static int loss_forward(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
                         const void* in_len, const void* tgt_len, void* losses, char* ws, cudaStream_t s) {
   E2E_CUDA_TRY(cudaMemsetAsync(ws + p.off_status, 0, p.off_flags, s));   // status word + the meet flags
-  int rc = launch_row_stats(d, logits, ws + p.off_stats, s);
+  const bool emis = p.kind == kPlanFused && p.emis_stride > 0;
+  int rc = launch_row_stats(d, logits, ws + p.off_stats, emis ? reinterpret_cast<double*>(ws + p.off_emis) : nullptr,
+                            p.emis_stride, targets, in_len, tgt_len, s);
   if (rc != E2E_OK) return rc;
   if (p.kind == kPlanSweep) return launch_sweep(d, p, logits, targets, in_len, tgt_len, losses, nullptr, 1.0, ws, s);
   return launch_fused(d, p, logits, targets, in_len, tgt_len, losses, nullptr, 1.0, ws, s);

@@ -79,7 +79,8 @@ struct LossPlan {
   int vpad;
   size_t smem;      // dynamic shared memory of the lattice kernel
   // byte offsets into the workspace
-  size_t off_status, off_meet, off_flags, off_stats, off_stash, off_post, total;
+  size_t off_status, off_meet, off_flags, off_stats, off_stash, off_post, off_emis, total;
+  int emis_stride;  // general kernel, gather mode: doubles per frame of the compact emission rows K1 writes (0: none)
 };
 
 // fused: the caller wants loss + gradient in one pass (dense mode is used when the alphabet allows it)
@@ -205,7 +206,8 @@ __device__ __forceinline__ int warp_max_int(int v) {
 #endif  // __CUDACC__
 
 // ------------------------------------------------------------------ kernel launchers ----------
-int launch_row_stats(const e2e_ctc_desc& d, const void* logits, void* stats, cudaStream_t s);
+int launch_row_stats(const e2e_ctc_desc& d, const void* logits, void* stats, double* emis, int emis_stride,
+                     const void* targets, const void* in_len, const void* tgt_len, cudaStream_t s);
 int launch_fused(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
                  const void* in_len, const void* tgt_len, void* losses, void* grads, double scale, char* ws,
                  cudaStream_t s);

@@ -16,6 +16,7 @@ int launch_fused(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, c
   fp.logits = logits; fp.dtype = d.dtype; fp.sb = d.logits_stride_b; fp.st = d.logits_stride_t;
   fp.grads = grads; fp.gsb = d.grads_stride_b; fp.gst = d.grads_stride_t; fp.scale = scale;
   fp.stats = ws + p.off_stats;
+  fp.emis = p.emis_stride > 0 ? reinterpret_cast<const double*>(ws + p.off_emis) : nullptr; fp.emis_stride = p.emis_stride;
   fp.post = reinterpret_cast<float*>(ws + p.off_post); fp.post_stride = p.post_stride; fp.cells = p.cells;
   fp.targets = targets; fp.tgt_is64 = d.targets_itype == E2E_I64; fp.ts_b = d.targets_stride_b;
   fp.in_len = in_len; fp.tgt_len = tgt_len; fp.len_is64 = d.lengths_itype == E2E_I64;

@@ -54,6 +54,7 @@ struct FzParams {
   const void* logits; int dtype; long long sb, st;
   void* grads; long long gsb, gst; double scale;
   const void* stats;                      // gather mode: row {max, logsumexp} from K1
+  const double* emis; int emis_stride;    // gather mode: compact emission rows from K1: [label 0 .. Lmax-1 | blank] per frame
   float* post; int post_stride, cells;    // gather mode: compact posteriors [B*T][post_stride], blank total at cells/2
   const void* targets; int tgt_is64; long long ts_b;
   const void* in_len; const void* tgt_len; int len_is64;
@@ -295,8 +296,10 @@ __device__ __noinline__ double fz_produce_dense_f64(const FzParams& p, const FzV
   return lse;
 }
 
-// gather mode: lanes over the labels, all the block's frames in flight per label (independent loads): E row =
-// [label 0 .. label Li-1 | zeros ... | blank at column 64*NB], with the row statistics K1 wrote
+// gather mode: K1 left every frame's emissions compact in global memory ([label 0 .. label Lmax-1 | blank], doubles:
+// ctc_rowstats.cu) while it had the row in hand, so staging a block is a coalesced copy of (L_i + 1) doubles per
+// frame, all the block's frames in flight per lane: E row = [label 0 .. label Li-1 | zeros ... | blank at column
+// 64*NB] in THIS sweep's label order (the backward sweep runs over the reversed labels).
 __device__ __forceinline__ double fz_produce_gather(const FzParams& p, const FzView& sv, int b, long long xbase, int Ti, int Li,
                                                     int i0, int lane, bool BWD) {
   constexpr int F = 8;   // == PB in gather mode
@@ -304,45 +307,31 @@ __device__ __forceinline__ double fz_produce_gather(const FzParams& p, const FzV
   const int bcol = 64 * L.NB;
   const int nf = min(F, Ti - i0);
   double lse = 0.0;
-  if (p.dtype == E2E_F64) {
-    for (int f = 0; f < nf; f++) {
-      const int i = i0 + f, t = BWD ? (Ti - 1 - i) : i;
-      const long long row = (long long)b * p.T + t;
-      const double m = reinterpret_cast<const double*>(p.stats)[2 * row], ls = reinterpret_cast<const double*>(p.stats)[2 * row + 1];
-      const double* xr = reinterpret_cast<const double*>(p.logits) + xbase + (long long)t * p.st;
-      double* Erow = sv.E + (size_t)(i & (L.R - 1)) * L.es;
-      for (int k = lane; k <= Li; k += 32) {
-        const bool isb = k == Li;
-        Erow[isb ? bcol : k] = exp((__ldg(xr + (isb ? p.blank : sv.lab[k])) - m) - ls);
-      }
-      if (lane == 0) lse += m + ls;
-    }
-    return lse;
-  }
-  float m[F], ls[F];
-  long long ro[F];
+  const double* er[F];
 #pragma unroll
   for (int f = 0; f < F; f++) {
     const int i = i0 + min(f, nf - 1), t = BWD ? (Ti - 1 - i) : i;
     const long long row = (long long)b * p.T + t;
-    const float2 st = __ldg(reinterpret_cast<const float2*>(p.stats) + row);
-    m[f] = st.x; ls[f] = st.y;
-    ro[f] = xbase + (long long)t * p.st;
-    if (lane == 0 && f < nf) lse += (double)st.x + (double)st.y;
+    er[f] = p.emis + row * p.emis_stride;
+    if (lane == 0 && f < nf && !p.from_logits) {   // log-prob input: the row normalisers go back into the loss
+      if (p.dtype == E2E_F64) lse += reinterpret_cast<const double*>(p.stats)[2 * row] + reinterpret_cast<const double*>(p.stats)[2 * row + 1];
+      else { const float2 st = __ldg(reinterpret_cast<const float2*>(p.stats) + row); lse += (double)st.x + (double)st.y; }
+    }
   }
   for (int k = lane; k <= Li; k += 32) {
     const bool isb = k == Li;
-    const int sym = isb ? p.blank : sv.lab[k];
+    const int src = isb ? p.Lmax : (BWD ? Li - 1 - k : k);
     const int col = isb ? bcol : k;
-    float x[F];
+    double x[F];
 #pragma unroll
-    for (int f = 0; f < F; f++) x[f] = fz_load_logit(p.logits, p.dtype, ro[f] + sym);
+    for (int f = 0; f < F; f++) x[f] = __ldcg(er[f] + src);
 #pragma unroll
     for (int f = 0; f < F; f++) {
       const int i = i0 + min(f, nf - 1);
-      sv.E[(size_t)(i & (L.R - 1)) * L.es + col] = fz_emission(x[f], m[f], ls[f], p.from_logits);
+      sv.E[(size_t)(i & (L.R - 1)) * L.es + col] = x[f];
     }
   }
+  (void)xbase;
   return lse;
 }
 
@@ -353,11 +342,15 @@ __device__ void fz_producer(const FzParams& p, const FzView& sv, int b, int Ti, 
   const int nblocks = (Ti + PB - 1) / PB;
   const long long xbase = (long long)b * p.sb;
   double lse = 0.0;
+  long long dbg_wait = 0, dbg_work = 0;
   for (int bi = pw; bi < nblocks; bi += L.NP) {
     const int need = bi * PB + PB - L.R;   // frames below `need` must have left the ring
+    const long long dbg_a = FZ_CLK();
     if (need > 0) {   // write-after-read on the ring rows: plain progress words
-      while (sv.ctl->lat_prog < need || fz_min_done(sv.ctl->comb_done, L.NC) < need) { if (L.nap) __nanosleep(L.nap); }
+      // dense mode: the combiners read the emission rows too (the softmax term of the gradient); gather mode: only the lattice does
+      while (sv.ctl->lat_prog < need || (!GATHER && fz_min_done(sv.ctl->comb_done, L.NC) < need)) { if (L.nap) __nanosleep(L.nap); }
     }
+    const long long dbg_b = FZ_CLK();
     if (GATHER) lse += fz_produce_gather(p, sv, b, xbase, Ti, Li, bi * PB, lane, BWD);
     else if (p.dtype == E2E_F64) lse += fz_produce_dense_f64(p, sv, xbase, Ti, bi * PB, lane, BWD);
     else {
@@ -368,7 +361,12 @@ __device__ void fz_producer(const FzParams& p, const FzView& sv, int b, int Ti, 
     }
     __syncwarp();
     if (lane == 0) fz_mbar_arrive(&sv.ctl->fullE[bi & L.neb_mask]);
+    dbg_wait += dbg_b - dbg_a; dbg_work += FZ_CLK() - dbg_b;
   }
+#ifdef FZ_DBG
+  if (blockIdx.x < 4 && lane == 0 && pw < 2) { g_fz_dbg[64 + blockIdx.x * 4 + pw * 2] = dbg_wait; g_fz_dbg[64 + blockIdx.x * 4 + pw * 2 + 1] = dbg_work; }
+#endif
+  (void)dbg_wait; (void)dbg_work;
   if (lane == 0) sv.ctl->lse[pw] = lse;   // lane 0 summed its frames in order: deterministic loss for log-prob input
 }
 
@@ -1098,6 +1096,8 @@ int launch_fused_k(const FzParams& fp, cudaStream_t s) {
     for (int c = 0; c < 4; c++) {
       fprintf(stderr, "[fz dbg] cta %d lattice loop %lld cyc (wait E %lld, wait comb %lld) T %lld NBU %lld | role cycles:", c, h[c * 8], h[c * 8 + 1], h[c * 8 + 2], h[c * 8 + 3], h[c * 8 + 4]);
       for (int w = 0; w < 8; w++) fprintf(stderr, " %lld", h[32 + c * 8 + w]);
+      fprintf(stderr, " | producers (ring wait, work):");
+      for (int q = 0; q < 2; q++) fprintf(stderr, " (%lld, %lld)", h[64 + c * 4 + q * 2], h[64 + c * 4 + q * 2 + 1]);
       fprintf(stderr, "\n");
     }
   }

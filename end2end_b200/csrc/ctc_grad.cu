@@ -26,19 +26,75 @@ struct GradParams {
   const void* targets; int tgt_is64; long long ts_b;
   const void* in_len; const void* tgt_len; int len_is64;
   const void* grad_out; int grad_out_count; double host_scale;
-  int B, T, V, Lmax, blank, from_logits, cells, post_stride, rows_per_block;
+  int B, T, V, Lmax, blank, from_logits, cells, post_stride, rows_per_block, vec_ok, vstride;
 };
 
 __device__ __forceinline__ float exp_acc(float x) { return expf(x); }
 __device__ __forceinline__ double exp_acc(double x) { return exp(x); }
 
+// 16-byte vectors of the element type (the row loops move 128 bits per lane per access when the rows are aligned)
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&o)[4]) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p)); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Vec16<double> {
+  static constexpr int N = 2;
+  static __device__ __forceinline__ void load(const double* p, double (&o)[2]) {
+    const double2 v = __ldg(reinterpret_cast<const double2*>(p)); o[0] = v.x; o[1] = v.y;
+  }
+  static __device__ __forceinline__ void store(double* p, const double (&v)[2]) { *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]); }
+};
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&o)[8]) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) { o[2 * i] = __uint_as_float(w[i] << 16); o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <> struct Vec16<__half> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __half* p, float (&o)[8]) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const float2 f = __half22float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+  }
+  static __device__ __forceinline__ void store(__half* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 ctc_grad_kernel(const GradParams p) {
   using acc_t = typename Elem<T>::acc_t;
+  constexpr int N = Vec16<T>::N;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int* s_lab = reinterpret_cast<int*>(smem_raw);
-  float* s_acc = reinterpret_cast<float*>(s_lab + p.Lmax + (p.Lmax & 1));
+  float* s_acc = reinterpret_cast<float*>(s_lab + ((p.Lmax + 3) & ~3));
 
   const int tiles = (p.T + p.rows_per_block - 1) / p.rows_per_block;
   const int b = blockIdx.x / tiles;
@@ -66,22 +122,46 @@ ctc_grad_kernel(const GradParams p) {
   const T* x = reinterpret_cast<const T*>(p.logits) + b * p.sb + t * p.st;
   T* g = reinterpret_cast<T*>(p.grads) + b * p.gsb + t * p.gst;
   const long long row = (long long)b * p.T + t;
+  const int nvec = p.vec_ok ? p.V / N : 0;     // 128-bit accesses over [0, nvec*N), scalar tail after
 
   if (flag) {  // infeasible (or rejected) utterance: NaN block, as -inf - (-inf) gives in the reference
-    for (int v = lane; v < p.V; v += 32) Elem<T>::store(g + v, (acc_t)NAN);
+    acc_t nanv[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) nanv[k] = (acc_t)NAN;
+    for (int i = lane; i < nvec; i += 32) Vec16<T>::store(g + i * N, nanv);
+    for (int v = nvec * N + lane; v < p.V; v += 32) Elem<T>::store(g + v, (acc_t)NAN);
     return;
   }
   if (t >= Ti) {  // padding frame
     if (p.from_logits) {
-      for (int v = lane; v < p.V; v += 32) Elem<T>::store(g + v, scale * (acc_t)0);
+      acc_t z[N];
+#pragma unroll
+      for (int k = 0; k < N; k++) z[k] = scale * (acc_t)0;
+      for (int i = lane; i < nvec; i += 32) Vec16<T>::store(g + i * N, z);
+      for (int v = nvec * N + lane; v < p.V; v += 32) Elem<T>::store(g + v, scale * (acc_t)0);
     } else {
-      for (int v = lane; v < p.V; v += 32) Elem<T>::store(g + v, scale * exp_acc(Elem<T>::load(x + v)));
+      for (int i = lane; i < nvec; i += 32) {
+        acc_t xv[N];
+        Vec16<T>::load(x + i * N, xv);
+#pragma unroll
+        for (int k = 0; k < N; k++) xv[k] = scale * exp_acc(xv[k]);
+        Vec16<T>::store(g + i * N, xv);
+      }
+      for (int v = nvec * N + lane; v < p.V; v += 32) Elem<T>::store(g + v, scale * exp_acc(Elem<T>::load(x + v)));
     }
     return;
   }
 
-  float* acc = s_acc + (size_t)w * p.V;
-  for (int v = lane; v < p.V; v += 32) acc[v] = 0.f;
+  // the row's logits are requested BEFORE the posterior scatter so that the HBM latency overlaps it
+  constexpr int PRE = 8;                      // vectors per lane held in registers: rows up to 32*N*PRE elements
+  acc_t xr[PRE][N];
+  const bool pre = nvec > 0 && nvec <= 32 * PRE;
+  if (pre) {
+#pragma unroll
+    for (int j = 0; j < PRE; j++) { const int i = j * 32 + lane; if (i < nvec) Vec16<T>::load(x + i * N, xr[j]); }
+  }
+  float* acc = s_acc + (size_t)w * p.vstride;
+  for (int v = lane * 4; v < p.vstride; v += 128) *reinterpret_cast<float4*>(acc + v) = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
   // compact posterior row written by the lattice kernel's combiners: [label 0 .. label L-1 | ... | blank total]
   const float* post = p.post + row * p.post_stride;
@@ -94,21 +174,46 @@ ctc_grad_kernel(const GradParams p) {
     m = reinterpret_cast<const acc_t*>(p.stats)[2 * row];
     ls = reinterpret_cast<const acc_t*>(p.stats)[2 * row + 1];
   }
-  for (int v = lane; v < p.V; v += 32) {
-    const acc_t xv = Elem<T>::load(x + v);
+  auto one = [&](acc_t xv, float a) {
     const acc_t first = p.from_logits ? exp_acc((xv - m) - ls) : exp_acc(xv);
-    Elem<T>::store(g + v, scale * (first - (acc_t)acc[v]));
+    return scale * (first - (acc_t)a);
+  };
+  if (pre) {
+#pragma unroll
+    for (int j = 0; j < PRE; j++) {
+      const int i = j * 32 + lane;
+      if (i < nvec) {
+        acc_t r[N];
+#pragma unroll
+        for (int k = 0; k < N; k++) r[k] = one(xr[j][k], acc[i * N + k]);
+        Vec16<T>::store(g + i * N, r);
+      }
+    }
+  } else {
+    for (int i = lane; i < nvec; i += 32) {
+      acc_t xv[N], r[N];
+      Vec16<T>::load(x + i * N, xv);
+#pragma unroll
+      for (int k = 0; k < N; k++) r[k] = one(xv[k], acc[i * N + k]);
+      Vec16<T>::store(g + i * N, r);
+    }
   }
+  for (int v = nvec * N + lane; v < p.V; v += 32) Elem<T>::store(g + v, one(Elem<T>::load(x + v), acc[v]));
 }
 
 template <typename T>
 int launch_typed(const GradParams& gp, cudaStream_t s) {
   GradParams p = gp;
-  const size_t lab_bytes = (size_t)(p.Lmax + (p.Lmax & 1)) * sizeof(int);
+  constexpr size_t vb = 16;
+  p.vec_ok = (reinterpret_cast<uintptr_t>(p.logits) % vb == 0) && (reinterpret_cast<uintptr_t>(p.grads) % vb == 0) &&
+             ((p.sb * sizeof(T)) % vb == 0) && ((p.st * sizeof(T)) % vb == 0) && ((p.gsb * sizeof(T)) % vb == 0) &&
+             ((p.gst * sizeof(T)) % vb == 0) && p.V >= 32;
+  p.vstride = (p.V + 3) & ~3;
+  const size_t lab_bytes = (size_t)((p.Lmax + 3) & ~3) * sizeof(int);
   int rpb = 8;
-  while (rpb > 1 && lab_bytes + (size_t)rpb * p.V * sizeof(float) > 96 * 1024) rpb >>= 1;
+  while (rpb > 1 && lab_bytes + (size_t)rpb * p.vstride * sizeof(float) > 96 * 1024) rpb >>= 1;
   p.rows_per_block = rpb;
-  const size_t smem = lab_bytes + (size_t)rpb * p.V * sizeof(float);
+  const size_t smem = lab_bytes + (size_t)rpb * p.vstride * sizeof(float);
   if (smem > 200 * 1024) {
     set_error("grad: alphabet %d too large for the shared-memory row accumulator", p.V);
     return E2E_ERR_UNSUPPORTED;

@@ -3,7 +3,8 @@
 // Replaces CTCDecoder::decode_greedy (src/decoders/ctc_decoder.cpp:443-490):
 //   K5a  argmax over the alphabet per frame (ctc_decoder.cpp:451, torch.argmax semantics: the FIRST
 //        maximum wins, a NaN is larger than every number and the first NaN wins); one warp per
-//        row, warp-shuffle (value,index) reduction, frames beyond the utterance length are not read;
+//        row, the row fetched with 128-bit loads that are all in flight at once, warp-shuffle (key,index)
+//        reduction, frames beyond the utterance length are not read;
 //   K5b  per utterance, emit frame t's symbol iff it is not blank and differs from frame t-1's
 //        (ctc_decoder.cpp:471-482) -- a warp-ballot / popc compaction scan over the frames -- into
 //        the zero-padded [B,T] int64 output, plus the decoded length.
@@ -17,36 +18,106 @@ namespace {
 
 constexpr int kRowsPerBlock = 8;
 
-template <typename A>
-__device__ __forceinline__ bool better(A va, int ia, A vb, int ib) {
-  // true when (va, ia) beats (vb, ib)
-  const bool na = va != va, nb = vb != vb;
-  if (na || nb) return na && (!nb || ia < ib);
-  return va > vb || (va == vb && ia < ib);
+// torch.argmax order as ONE unsigned key per value: larger key = better; NaN is the largest key; -0.0 and +0.0
+// compare equal (x + 0 canonicalises the zero) so that ties between them fall to the lower index, as in torch.
+__device__ __forceinline__ uint32_t order_key(float x) {
+  if (x != x) return 0xffffffffu;
+  const uint32_t u = __float_as_uint(x + 0.0f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
+__device__ __forceinline__ unsigned long long order_key(double x) {
+  if (x != x) return ~0ull;
+  const unsigned long long u = (unsigned long long)__double_as_longlong(x + 0.0);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+template <typename K> struct KeyShfl;
+template <> struct KeyShfl<uint32_t> {
+  static __device__ __forceinline__ uint32_t xor_(uint32_t k, int o) { return __shfl_xor_sync(0xffffffffu, k, o); }
+};
+template <> struct KeyShfl<unsigned long long> {
+  static __device__ __forceinline__ unsigned long long xor_(unsigned long long k, int o) { return __shfl_xor_sync(0xffffffffu, k, o); }
+};
 
-template <typename T>
+// 16-byte vector loads of the element type, widened to the compare type
+template <typename T> struct GVec;
+template <> struct GVec<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&o)[4]) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p)); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+};
+template <> struct GVec<double> {
+  static constexpr int N = 2;
+  static __device__ __forceinline__ void load(const double* p, double (&o)[2]) {
+    const double2 v = __ldg(reinterpret_cast<const double2*>(p)); o[0] = v.x; o[1] = v.y;
+  }
+};
+template <> struct GVec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&o)[8]) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) { o[2 * i] = __uint_as_float(w[i] << 16); o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  }
+};
+template <> struct GVec<__half> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __half* p, float (&o)[8]) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const float2 f = __half22float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+  }
+};
+
+// One warp per frame row.  NV > 0: the row (<= 32*N*NV symbols, 16-byte aligned) is fetched with NV 128-bit loads
+// per lane, all in flight at once; NV == 0: scalar streaming loop (unaligned rows, huge alphabets).  A lane walks its
+// symbols in increasing index order, so a strict > keeps the first maximum; across lanes the lower index breaks ties.
+template <typename T, int NV>
 __global__ void __launch_bounds__(kRowsPerBlock * 32)
 ctc_argmax_kernel(const T* __restrict__ logits, long long sb, long long st, int B, int T_, int V,
                   const void* in_len, int len_is64, int* __restrict__ sym) {
   using acc_t = typename Elem<T>::acc_t;
+  using key_t = decltype(order_key(acc_t(0)));
+  constexpr int N = GVec<T>::N;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
   if (row >= (long long)B * T_) return;
   const int b = (int)(row / T_), t = (int)(row % T_);
   if (in_len != nullptr && t >= load_index(in_len, len_is64, b)) return;
   const T* x = logits + b * sb + t * st;
-  acc_t bv = -INFINITY;
+  key_t bk = 0;              // below every real key (the smallest is ~(-inf bits) > 0 ... see below): index decides
   int bi = 0x7fffffff;
-  for (int v = lane; v < V; v += 32) {
-    const acc_t xv = Elem<T>::load(x + v);
-    if (bi == 0x7fffffff || better(xv, v, bv, bi)) { bv = xv; bi = v; }
+  if (NV > 0) {
+    acc_t v[NV > 0 ? NV : 1][N];
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+      const int i = (j * 32 + lane) * N;
+      if (i < V) GVec<T>::load(x + i, v[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+      const int i = (j * 32 + lane) * N;
+      if (i < V) {
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+          const key_t kk = order_key(v[j][k]);
+          if (bi == 0x7fffffff || kk > bk) { bk = kk; bi = i + k; }
+        }
+      }
+    }
+  } else {
+    for (int i = lane; i < V; i += 32) {
+      const key_t kk = order_key(Elem<T>::load(x + i));
+      if (bi == 0x7fffffff || kk > bk) { bk = kk; bi = i; }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    const acc_t ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const key_t ok = KeyShfl<key_t>::xor_(bk, o);
     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (oi != 0x7fffffff && (bi == 0x7fffffff || better(ov, oi, bv, bi))) { bv = ov; bi = oi; }
+    if (oi != 0x7fffffff && (bi == 0x7fffffff || ok > bk || (ok == bk && oi < bi))) { bk = ok; bi = oi; }
   }
   if (lane == 0) sym[row] = bi;
 }
@@ -93,12 +164,18 @@ ctc_collapse_kernel(const int* __restrict__ sym, int T_, int blank, const void* 
 
 template <typename T>
 int launch_typed(const e2e_ctc_desc& d, const void* logits, const void* in_len, int* sym, cudaStream_t s) {
+  constexpr int N = GVec<T>::N;
   const long long rows = (long long)d.batch * d.max_frames;
   const unsigned grid = (unsigned)((rows + kRowsPerBlock - 1) / kRowsPerBlock);
+  const int V = d.alphabet;
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(logits) % 16 == 0) && ((d.logits_stride_b * sizeof(T)) % 16 == 0) &&
+                      ((d.logits_stride_t * sizeof(T)) % 16 == 0) && V % N == 0 && V <= 32 * N * 8;
+  const int nv = vec_ok ? (V + 32 * N - 1) / (32 * N) : 0;
   KernelTimer timer(kKernelArgmax, s);
-  ctc_argmax_kernel<T><<<grid, kRowsPerBlock * 32, 0, s>>>(
-      reinterpret_cast<const T*>(logits), d.logits_stride_b, d.logits_stride_t, d.batch, d.max_frames,
-      d.alphabet, in_len, d.lengths_itype == E2E_I64, sym);
+#define E2E_K5(NV) ctc_argmax_kernel<T, NV><<<grid, kRowsPerBlock * 32, 0, s>>>(reinterpret_cast<const T*>(logits), d.logits_stride_b, \
+      d.logits_stride_t, d.batch, d.max_frames, V, in_len, d.lengths_itype == E2E_I64, sym)
+  if (nv == 0) E2E_K5(0); else if (nv == 1) E2E_K5(1); else if (nv == 2) E2E_K5(2); else if (nv <= 4) E2E_K5(4); else E2E_K5(8);
+#undef E2E_K5
   E2E_CUDA_TRY(cudaGetLastError());
   return E2E_OK;
 }
