@@ -26,8 +26,9 @@ EXPORTS = (
     "e2e_ctc_profile_enable", "e2e_ctc_profile_read",
     "e2e_ctc_comm_unique_id", "e2e_ctc_comm_create", "e2e_ctc_comm_destroy", "e2e_ctc_comm_allreduce_sum",
     "e2e_ctc_graph_create", "e2e_ctc_graph_launch", "e2e_ctc_graph_destroy",
+    "e2e_ctc_viterbi_workspace_bytes", "e2e_ctc_viterbi_align_device",
 )
-KERNEL_KINDS = ("row_stats", "lattice", "gradient", "loss_reduce", "argmax", "collapse", "scale_rows")
+KERNEL_KINDS = ("row_stats", "lattice", "gradient", "loss_reduce", "argmax", "collapse", "scale_rows", "viterbi")
 
 
 class Desc(ctypes.Structure):
@@ -100,6 +101,10 @@ def load():
     L.e2e_ctc_comm_destroy.restype = None
     L.e2e_ctc_comm_allreduce_sum.argtypes = [vp, vp, ctypes.c_int64, i32, vp]
     L.e2e_ctc_graph_create.argtypes = [dp, vp, vp, vp, vp, vp, vp, dbl, vp, vp, dbl, vp, sz, vp, ctypes.POINTER(vp)]
+    L.e2e_ctc_viterbi_workspace_bytes.argtypes = [dp, i32]
+    L.e2e_ctc_viterbi_workspace_bytes.restype = sz
+    L.e2e_ctc_viterbi_align_device.argtypes = [dp, i32, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.e2e_ctc_viterbi_align_device.restype = ctypes.c_int
     L.e2e_ctc_graph_launch.argtypes = [vp, vp]
     L.e2e_ctc_graph_destroy.argtypes = [vp]
     L.e2e_ctc_graph_destroy.restype = None

@@ -148,7 +148,8 @@ static bool make_sweep_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   };
   int cf = 32;
   // several CTAs per SM when the batch is large; otherwise whatever fits
-  const size_t want = d.batch > 148 ? 56 * 1024 : 200 * 1024;
+  static const int want_kb = env_int("E2E_CTC_SWEEP_SMEM_KB", 0);   // experiments only
+  const size_t want = want_kb > 0 ? (size_t)want_kb * 1024 : (d.batch > 148 ? 56 * 1024 : 200 * 1024);
   while (cf > 8 && layout(cf) > want) cf >>= 1;
   const size_t smem = layout(cf);
   if (smem > 220 * 1024) return false;
@@ -286,7 +287,7 @@ static bool make_fused_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   L.R = 2 * L.PB;                                 // at least two producer blocks in the ring, four when they fit 32 KB
   // gather mode: four blocks -- a producer's block is two dependent L2 round trips (~4k cycles), twice what the sweep
   // needs for a block, so with two blocks in the ring the lattice warp waited for emissions 45 % of its time (measured)
-  if ((size_t)4 * L.PB * L.es * 8 <= 32 * 1024 || !dense) L.R = 4 * L.PB;
+  if ((size_t)4 * L.PB * L.es * 8 <= (size_t)(dense ? 32 : 48) * 1024) L.R = 4 * L.PB;
   while (L.R < 128 && (size_t)2 * L.R * L.es * 8 <= (size_t)(latency ? 48 : 24) * 1024) L.R *= 2;
   if (tn.r >= 2 * L.PB && !(tn.r & (tn.r - 1))) L.R = tn.r;
   if (L.R > 16 * L.PB) L.R = 16 * L.PB;   // at most 16 emission blocks (one mbarrier each)
@@ -598,6 +599,27 @@ int e2e_ctc_greedy_decode_device(const e2e_ctc_desc* desc, const void* logits, c
   if (rc != E2E_OK) return rc;
   return launch_greedy(*desc, logits, logits_lengths, decoded, decoded_lengths,
                        reinterpret_cast<char*>(workspace), reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+// ---- Viterbi forced alignment -------------------------------------------------------
+size_t e2e_ctc_viterbi_workspace_bytes(const e2e_ctc_desc* desc, int32_t is_ctc) {
+  if (check_desc(desc, true) != E2E_OK) return 0;
+  return align256(viterbi_workspace_bytes(*desc, is_ctc ? 1 : 0));
+}
+
+int e2e_ctc_viterbi_align_device(const e2e_ctc_desc* desc, int32_t is_ctc, const void* log_probs, const void* targets,
+                                 const void* logits_lengths, const void* targets_lengths, int64_t* aligned,
+                                 void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  int rc = check_desc(desc, true);
+  if (rc != E2E_OK) return rc;
+  if (!log_probs || !logits_lengths || !targets_lengths || !aligned || (!targets && desc->max_targets > 0)) {
+    set_error("null pointer argument");
+    return E2E_ERR_INVALID_ARGUMENT;
+  }
+  rc = check_ws(workspace, workspace_bytes, e2e_ctc_viterbi_workspace_bytes(desc, is_ctc));
+  if (rc != E2E_OK) return rc;
+  return launch_viterbi(*desc, is_ctc ? 1 : 0, log_probs, targets, logits_lengths, targets_lengths, aligned,
+                        reinterpret_cast<char*>(workspace), reinterpret_cast<cudaStream_t>(cuda_stream));
 }
 
 // ---- CUDA-graph step ------------------------------------------------------------------------------

@@ -186,6 +186,21 @@ int e2e_ctc_graph_create(const e2e_ctc_desc* desc, const void* logits, const voi
 int e2e_ctc_graph_launch(e2e_ctc_graph* graph, void* cuda_stream);
 void e2e_ctc_graph_destroy(e2e_ctc_graph* graph);
 
+/* ------------------------------------------------------------ Viterbi forced alignment ----- */
+
+/* Best-path (Viterbi) alignment of every utterance's targets to its frames -- the reference's
+ * pytorch_end2end/utils/alignment.py: get_alignment_3d (:109-138) over _get_alignment_ctc_1d (:50-106, is_ctc != 0:
+ * blank-extended lattice) or _get_alignment_asg_1d (:9-47, is_ctc == 0: labels only).  `log_probs` are
+ * log-probabilities [B,T,V] (desc strides), `aligned` is [B,T] int64: the label id of every frame, -100 past the
+ * utterance's frames (the reference's fill value).  Bit-exact with the reference: fp64 max-plus recursion with its
+ * comparison order and window.  desc->blank_idx is the blank (the reference hard-codes 0).  A logits length of 0
+ * leaves the row at -100; out-of-range lengths / labels set status bits (e2e_ctc_loss_check_device on the
+ * workspace) and leave -100. */
+size_t e2e_ctc_viterbi_workspace_bytes(const e2e_ctc_desc* desc, int32_t is_ctc);
+int e2e_ctc_viterbi_align_device(const e2e_ctc_desc* desc, int32_t is_ctc, const void* log_probs,
+                                 const void* targets, const void* logits_lengths, const void* targets_lengths,
+                                 int64_t* aligned, void* workspace, size_t workspace_bytes, void* cuda_stream);
+
 /* --------------------------------------------------------------- greedy decode, device ----- */
 
 size_t e2e_ctc_greedy_workspace_bytes(const e2e_ctc_desc* desc);

@@ -52,6 +52,9 @@ def lib():
         L.ctc_oracle_log_softmax_f32.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.c_int64,
                                                  ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
         L.ctc_oracle_log_softmax_f32.restype = None
+        L.ctc_oracle_align.argtypes = [dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ip, ctypes.c_int, ip, ip,
+                                       ctypes.c_int, ctypes.c_int, ip]
+        L.ctc_oracle_align.restype = None
         _lib = L
     return _lib
 
@@ -223,3 +226,18 @@ CONFIGS = {
     "c4": (128, 250, 1024, 40, 80, 3, torch.float32, False),
     "c5": (2048, 1600, 29, 300, 600, 4, torch.float32, False),
 }
+
+
+def get_alignment_3d(log_probs, targets, logits_lengths, targets_lengths, is_ctc=True, blank_idx=0):
+    """pytorch_end2end/utils/alignment.py:109-138 through the C restatement: CPU int64 [B, T], -100 past the frames."""
+    lp = np.ascontiguousarray(log_probs.detach().to("cpu").to(torch.float64).numpy())
+    B, T, V = lp.shape
+    tg = np.ascontiguousarray(targets.to("cpu").to(torch.int64).numpy()).reshape(B, -1)
+    Lmax = tg.shape[1]
+    if Lmax == 0:
+        tg, Lmax = np.zeros((B, 1), dtype=np.int64), 1
+    il = np.ascontiguousarray(logits_lengths.to("cpu").to(torch.int64).numpy())
+    tl = np.ascontiguousarray(targets_lengths.to("cpu").to(torch.int64).numpy())
+    out = np.zeros((B, T), dtype=np.int64)
+    lib().ctc_oracle_align(_dptr(lp), B, T, V, _iptr(tg), Lmax, _iptr(il), _iptr(tl), int(blank_idx), 1 if is_ctc else 0, _iptr(out))
+    return torch.from_numpy(out)

@@ -23,6 +23,10 @@
  *                                                              maximal -- torch's rule) then
  *                                                              collapse repeats / drop blanks
  *   ctc_oracle_log_softmax_f32() <- pytorch_end2end/modules/ctc_loss.py:40 (F.log_softmax, fp32)
+ *   ctc_oracle_align()     <- pytorch_end2end/utils/alignment.py:50-106 (_get_alignment_ctc_1d), :9-47
+ *                                                              (_get_alignment_asg_1d), :109-138 (batch driver,
+ *                                                              -100 fill); pinned by tests/golden/align_*.npz,
+ *                                                              made by running the reference's numba code
  *
  * Storage is frame-major ([T][S]) here, where the reference keeps [S][T]; the arithmetic and the
  * order of the chained two-argument log-sum-exp calls are the reference's.
@@ -175,5 +179,77 @@ void ctc_oracle_greedy(const double* logits, int B, int T, int V, const int64_t*
       prev = best;
     }
     out_len[b] = n;
+  }
+}
+
+/*
+ * Viterbi forced alignment, one utterance.  lp: [T][V] log-probabilities as doubles (the reference adds the
+ * float32 inputs into a float64 matrix: the same values).  out: [T] label ids.
+ * alignment.py:50-106 (is_ctc) / :9-47 (ASG); blank is 0 in the reference, a parameter here.
+ */
+static void align_utterance(const double* lp, int V, const int64_t* targets, int T, int L, int blank, int is_ctc,
+                            int64_t* out) {
+  for (int k = 0; k < T; k++) out[k] = 0;                               /* np.zeros(prediction_len) */
+  if (T == 0) return;
+  if (is_ctc) {
+    const int S = 2 * L + 1;
+    if (S == 1) return;                                                 /* only blank: zeros (:68-70) */
+    if (T == 1) { out[0] = targets[0]; return; }                         /* :71-73 */
+    int64_t* ext = (int64_t*)malloc(sizeof(int64_t) * (size_t)S);
+    for (int i = 0; i < S; i++) ext[i] = (i & 1) ? targets[i / 2] : (int64_t)blank;
+    double* alpha = (double*)malloc(sizeof(double) * (size_t)S * (size_t)T);
+    int* path = (int*)calloc((size_t)S * (size_t)T, sizeof(int));        /* np.zeros_like: 0 outside the window */
+    for (size_t q = 0; q < (size_t)S * (size_t)T; q++) alpha[q] = NEG_INF;
+#define A(i, k) alpha[(size_t)(i) * T + (k)]
+#define P(i, k) path[(size_t)(i) * T + (k)]
+    A(0, 0) = lp[ext[0]];
+    A(1, 0) = lp[ext[1]];
+    for (int k = 1; k < T; k++) {
+      const int start = imax(0, S - 2 * (T - k)), end = imin(k * 2 + 2, S);
+      for (int i = start; i < end; i++) { A(i, k) = A(i, k - 1); P(i, k) = i; }
+      for (int i = start; i < end; i++) {
+        const int64_t cur = ext[i];
+        if (i > 0) {
+          if (A(i - 1, k - 1) > A(i, k)) { A(i, k) = A(i - 1, k - 1); P(i, k) = i - 1; }
+          if (cur != blank && i - 2 > 0 && ext[i - 2] != cur && A(i - 2, k - 1) > A(i, k)) { A(i, k) = A(i - 2, k - 1); P(i, k) = i - 2; }
+        }
+        A(i, k) += lp[(size_t)k * V + cur];
+      }
+    }
+    int i = S - 1;
+    if (A(i - 1, T - 1) > A(i, T - 1)) i = i - 1;
+    for (int k = T - 1; k >= 0; k--) { out[k] = ext[i]; i = P(i, k); }
+    free(ext); free(alpha); free(path);
+  } else {
+    if (L == 0) return;
+    if (T == 1) { out[0] = targets[0]; return; }                         /* :20-22 */
+    double* alpha = (double*)malloc(sizeof(double) * (size_t)L * (size_t)T);
+    int* path = (int*)calloc((size_t)L * (size_t)T, sizeof(int));
+    for (size_t q = 0; q < (size_t)L * (size_t)T; q++) alpha[q] = NEG_INF;
+    A(0, 0) = lp[targets[0]];
+    for (int k = 1; k < T; k++) {
+      const int start = imax(0, L - (T - k)), end = imin(k + 1, L);
+      for (int i = start; i < end; i++) { A(i, k) = A(i, k - 1); P(i, k) = i; }
+      for (int i = start; i < end; i++) {
+        if (i > 0 && A(i - 1, k - 1) > A(i, k)) { A(i, k) = A(i - 1, k - 1); P(i, k) = i - 1; }
+        A(i, k) += lp[(size_t)k * V + targets[i]];
+      }
+    }
+    int i = L - 1;
+    for (int k = T - 1; k >= 0; k--) { out[k] = targets[i]; i = P(i, k); }
+    free(alpha); free(path);
+#undef A
+#undef P
+  }
+}
+
+/* get_alignment_3d (alignment.py:109-138): out [B][T] int64, -100 past every utterance's frames. */
+void ctc_oracle_align(const double* lp, int B, int T, int V, const int64_t* targets, int Lmax, const int64_t* in_len,
+                      const int64_t* tgt_len, int blank, int is_ctc, int64_t* out) {
+#pragma omp parallel for schedule(dynamic)
+  for (int b = 0; b < B; b++) {
+    int64_t* o = out + (size_t)b * T;
+    for (int k = 0; k < T; k++) o[k] = -100;
+    align_utterance(lp + (size_t)b * T * V, V, targets + (size_t)b * Lmax, (int)in_len[b], (int)tgt_len[b], blank, is_ctc, o);
   }
 }

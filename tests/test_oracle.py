@@ -164,3 +164,20 @@ def test_log_softmax_restatement():
     x = torch.randn(50, 29, generator=torch.Generator().manual_seed(0))
     out = torch.from_numpy(oracle.log_softmax_f32(x.numpy()))
     assert torch.allclose(out, torch.log_softmax(x, -1), rtol=0, atol=1e-6)
+
+
+# --------------------------------------------------------------------------------------------
+# Viterbi forced alignment: the C restatement against vectors the reference's own
+# numba code produced (tests/golden/make_align_golden.py)
+# --------------------------------------------------------------------------------------------
+ALIGN_GOLDENS = ["align_c1", "align_c2_b8", "align_c2_b4_peaky", "align_c4_b2", "align_c5_b2", "align_asg_c1",
+                 "align_asg_c2_b4", "align_edge", "align_asg_edge"]
+
+
+@pytest.mark.parametrize("name", ALIGN_GOLDENS)
+def test_alignment_oracle_matches_reference_goldens(name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    out = oracle.get_alignment_3d(torch.from_numpy(g["log_probs"]), torch.from_numpy(g["targets"]),
+                                  torch.from_numpy(g["logits_lengths"]), torch.from_numpy(g["targets_lengths"]),
+                                  is_ctc=bool(g["is_ctc"]))
+    assert out.dtype == torch.int64 and torch.equal(out, torch.from_numpy(g["aligned"]))
