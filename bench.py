@@ -608,6 +608,57 @@ def run_ours(args, wl):
                                 "e2e_value": g_e2e, "l2": "two distinct 131 MB logit blocks alternate (> 126 MB L2)"}
             del gx, hxg
             torch.cuda.empty_cache()
+            # ---- Viterbi forced alignment of the c2 batch's log-probabilities ----
+            from end2end_b200.utils.alignment import get_alignment_3d_device
+            import oracle
+            Ba, Ta, Va, Lmin, Lmax, seed = WORKLOADS["c2"][:6]
+            ax, atg, all_, atl = make_inputs(Ba, Ta, Va, Lmin, Lmax, seed, torch.float32, False)
+            alp = torch.log_softmax(ax, 2)
+            dlp, dtg, dll, dtl = alp.to(dev), atg.to(dev), all_.to(dev), atl.to(dev)
+            got = get_alignment_3d_device(dlp, dtg, dll, dtl)
+            want = oracle.get_alignment_3d(alp, atg, all_, atl)
+            assert torch.equal(got.cpu(), want), "alignment differs from the oracle"
+            _lib.profile_enable(True); _lib.profile_read()
+            for i in range(20):
+                flush_buf.add_(1)
+                get_alignment_3d_device(dlp, dtg, dll, dtl)
+            torch.cuda.synchronize()
+            aprof = _lib.profile_read(); _lib.profile_enable(False)
+            a_ms = aprof["viterbi"][0] / max(1, aprof["viterbi"][1])
+            t0 = time.perf_counter()
+            for _ in range(3):
+                oracle.get_alignment_3d(alp, atg, all_, atl)
+            a_cpu = Ba * 3 / (time.perf_counter() - t0)
+            # ---- CTC without blank on the same log-probabilities ----
+            from end2end_b200.functions.ctc_without_blank import ctc_without_blank_3d_loss
+            nl, ng = ctc_without_blank_3d_loss(dlp, dtg, dll, dtl, -1)
+            rl, rg = oracle.ctc_without_blank(alp, atg, all_, atl, -1)
+            n_err = float((ng.cpu().double() - rg).abs().max())
+            assert n_err <= 1e-5 and float((nl.cpu().double() - rl).abs().max()) <= 1e-5 * float(rl.abs().max()) + 1e-5, "ctc_without_blank differs from the oracle"
+            _lib.profile_enable(True); _lib.profile_read()
+            for i in range(10):
+                flush_buf.add_(1)
+                ctc_without_blank_3d_loss(dlp, dtg, dll, dtl, -1)
+            torch.cuda.synchronize()
+            nprof = _lib.profile_read(); _lib.profile_enable(False)
+            n_ms = nprof["ctc_without_blank"][0] / max(1, nprof["ctc_without_blank"][1])
+            t0 = time.perf_counter()
+            for _ in range(2):
+                oracle.ctc_without_blank(alp, atg, all_, atl, -1)
+            n_cpu = Ba * 2 / (time.perf_counter() - t0)
+            extras["ctc_without_blank"] = {"workload": "CTC-without-blank loss + gradient of the c2 batch, B=%d T=%d V=%d fp32 log-probs, space_idx=-1" % (Ba, Ta, Va),
+                                           "value": Ba / (n_ms * 1e-3), "unit": "utterances/s", "kernel_ms": n_ms, "max_grad_err_vs_oracle": n_err,
+                                           "algorithmic_bytes": 2 * Ba * Ta * Va * 4, "frac": 2 * Ba * Ta * Va * 4 / (n_ms * 1e-3) / 1e9 / peak,
+                                           "cpu_baseline": {"value": n_cpu, "unit": "utterances/s", "kind": "port", "cores": os.cpu_count(),
+                                                            "sample": "2 passes of the same batch, C restatement of the reference's numba code, OpenMP over utterances"}}
+            a_bytes = Ba * Ta * Va * 4 + Ba * Ta * 8
+            extras["alignment"] = {"workload": "Viterbi forced alignment (CTC lattice) of the c2 batch, B=%d T=%d V=%d fp32 log-probs" % (Ba, Ta, Va),
+                                   "value": Ba / (a_ms * 1e-3), "unit": "utterances/s", "kernel_ms": a_ms, "bit_exact_vs_oracle": True,
+                                   "algorithmic_bytes": a_bytes, "frac": a_bytes / (a_ms * 1e-3) / 1e9 / peak,
+                                   "l2": "L2 flushed between launches (256 MB write), kernel timed by the library's event hooks",
+                                   "cpu_baseline": {"value": a_cpu, "unit": "utterances/s", "kind": "port", "cores": os.cpu_count(),
+                                                    "sample": "3 passes of the same batch, C restatement of the reference's numba code, "
+                                                              "OpenMP over utterances (the reference: one Python thread per utterance)"}}
         if not args.no_cpu_baseline:
             best, runs = measure_reference(wl, 0, 1, args.ref_batch, cpu_seconds=args.cpu_seconds / 2, greedy=False)
             if best:

@@ -27,8 +27,9 @@ EXPORTS = (
     "e2e_ctc_comm_unique_id", "e2e_ctc_comm_create", "e2e_ctc_comm_destroy", "e2e_ctc_comm_allreduce_sum",
     "e2e_ctc_graph_create", "e2e_ctc_graph_launch", "e2e_ctc_graph_destroy",
     "e2e_ctc_viterbi_workspace_bytes", "e2e_ctc_viterbi_align_device",
+    "e2e_ctc_noblank_workspace_bytes", "e2e_ctc_noblank_fwd_bwd_device",
 )
-KERNEL_KINDS = ("row_stats", "lattice", "gradient", "loss_reduce", "argmax", "collapse", "scale_rows", "viterbi")
+KERNEL_KINDS = ("row_stats", "lattice", "gradient", "loss_reduce", "argmax", "collapse", "scale_rows", "viterbi", "ctc_without_blank")
 
 
 class Desc(ctypes.Structure):
@@ -105,6 +106,10 @@ def load():
     L.e2e_ctc_viterbi_workspace_bytes.restype = sz
     L.e2e_ctc_viterbi_align_device.argtypes = [dp, i32, vp, vp, vp, vp, vp, vp, sz, vp]
     L.e2e_ctc_viterbi_align_device.restype = ctypes.c_int
+    L.e2e_ctc_noblank_workspace_bytes.argtypes = [dp]
+    L.e2e_ctc_noblank_workspace_bytes.restype = sz
+    L.e2e_ctc_noblank_fwd_bwd_device.argtypes = [dp, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.e2e_ctc_noblank_fwd_bwd_device.restype = ctypes.c_int
     L.e2e_ctc_graph_launch.argtypes = [vp, vp]
     L.e2e_ctc_graph_destroy.argtypes = [vp]
     L.e2e_ctc_graph_destroy.restype = None

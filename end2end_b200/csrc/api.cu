@@ -185,8 +185,13 @@ static bool make_wave_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   L.NC = NW >= 4 ? 6 : 2;
   L.NP = NW >= 4 ? 2 : 1;
   if (L.NC < 1 || L.NC > 8 || (L.NP != 1 && L.NP != 2 && L.NP != 4)) return false;
-  L.nap = 32;
-  L.by_smsp = 0;
+  // experiment knobs (read once per process; a production process never sets them)
+  static const int wv_nc = env_int("E2E_CTC_WAVE_NC", 0), wv_np = env_int("E2E_CTC_WAVE_NP", 0), wv_nap = env_int("E2E_CTC_WAVE_NAP", -1),
+                   wv_smsp = env_int("E2E_CTC_WAVE_BY_SMSP", 0), wv_r = env_int("E2E_CTC_WAVE_R", 0), wv_rv = env_int("E2E_CTC_WAVE_RV", 0);
+  if (wv_nc >= 1 && wv_nc <= 8) L.NC = wv_nc;
+  if (wv_np == 1 || wv_np == 2 || wv_np == 4) L.NP = wv_np;
+  L.nap = wv_nap >= 0 ? wv_nap : 32;
+  L.by_smsp = wv_smsp ? 1 : 0;
   if (L.by_smsp) {
     int r = NW > L.NP ? NW : L.NP;
     if ((L.NC + 1) / 2 > r) r = (L.NC + 1) / 2;
@@ -199,7 +204,9 @@ static bool make_wave_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   L.es = (d.alphabet + 2) | 1;   // odd: the producer's lane-per-frame stores are bank-conflict free
   L.vpad = (d.alphabet + 3) & ~3;
   L.RV = lanes * K >= 1024 ? 16 : 32;
+  if (wv_rv == 8 || wv_rv == 16 || wv_rv == 32 || wv_rv == 64) L.RV = wv_rv;
   L.R = 128;   // producer blocks are 32 frames: two per producer in flight
+  if (wv_r == 64 || wv_r == 128 || wv_r == 256) L.R = wv_r;
   if (L.R < 64 || (L.R & (L.R - 1))) return false;
   while (L.R > 64 && (size_t)L.R * L.es * 8 > (size_t)(NW >= 4 ? 64 : 40) * 1024) L.R >>= 1;
   if (L.RV > L.R / 2) L.RV = L.R / 2;
@@ -619,6 +626,35 @@ int e2e_ctc_viterbi_align_device(const e2e_ctc_desc* desc, int32_t is_ctc, const
   rc = check_ws(workspace, workspace_bytes, e2e_ctc_viterbi_workspace_bytes(desc, is_ctc));
   if (rc != E2E_OK) return rc;
   return launch_viterbi(*desc, is_ctc ? 1 : 0, log_probs, targets, logits_lengths, targets_lengths, aligned,
+                        reinterpret_cast<char*>(workspace), reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+// ---- CTC without blank ---------------------------------------------------------------
+size_t e2e_ctc_noblank_workspace_bytes(const e2e_ctc_desc* desc) {
+  if (!desc || desc->batch < 1 || desc->max_frames < 1 || desc->alphabet < 1 || desc->max_targets < 0 || elem_size(desc->dtype) == 0) {
+    set_error("bad descriptor");
+    return 0;
+  }
+  return align256(noblank_workspace_bytes(*desc));
+}
+
+int e2e_ctc_noblank_fwd_bwd_device(const e2e_ctc_desc* desc, int32_t space_idx, const void* log_probs, const void* targets,
+                                   const void* logits_lengths, const void* targets_lengths, void* losses, void* grads,
+                                   void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  const size_t need = e2e_ctc_noblank_workspace_bytes(desc);
+  if (!need) return E2E_ERR_INVALID_ARGUMENT;
+  if (!log_probs || !logits_lengths || !targets_lengths || !losses || !grads || (!targets && desc->max_targets > 0)) {
+    set_error("null pointer argument");
+    return E2E_ERR_INVALID_ARGUMENT;
+  }
+  if (space_idx < -1 || space_idx >= desc->alphabet) { set_error("space_idx %d outside [-1,%d)", space_idx, desc->alphabet); return E2E_ERR_INVALID_ARGUMENT; }
+  if ((desc->lengths_itype != E2E_I32 && desc->lengths_itype != E2E_I64) || (desc->targets_itype != E2E_I32 && desc->targets_itype != E2E_I64)) {
+    set_error("bad index type");
+    return E2E_ERR_INVALID_ARGUMENT;
+  }
+  int rc = check_ws(workspace, workspace_bytes, need);
+  if (rc != E2E_OK) return rc;
+  return launch_noblank(*desc, space_idx, log_probs, targets, logits_lengths, targets_lengths, losses, grads,
                         reinterpret_cast<char*>(workspace), reinterpret_cast<cudaStream_t>(cuda_stream));
 }
 

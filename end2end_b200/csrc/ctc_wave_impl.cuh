@@ -107,6 +107,11 @@ __device__ __forceinline__ int wv_ld_acquire(const volatile int* p) {
   return r;
 }
 __device__ __forceinline__ double wv_hi2d(uint32_t h) { return __hiloint2double((int)h, 0); }
+// A stashed row is written once and read once: after the read its L2 lines are dead.  Dropping them (no write-back)
+// keeps the stash -- 33 MB per c2 launch, L2-resident between its write and its read -- out of DRAM altogether.
+__device__ __forceinline__ void wv_discard_l2_128(const void* p) {
+  asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+}
 
 // p(t, v) relative to the row's log-sum-exp, as a double: the exponent argument is formed as torch's fp32
 // log_softmax does ((x - max) - logsum, fp32) for raw logits, so the emission equals exp(double(lp32)) of the
@@ -559,6 +564,10 @@ __device__ void wave_combiner(const WaveParams& p, const WaveView& sv, int b, in
     wait_val(i);
     { const long long t0 = WV_CLK(); wv_cp_async_wait<PF - 1>(); __syncwarp(); WV_DBG_ADD(5, WV_CLK() - t0); }
     const uint32_t* orow = stage + (size_t)(k % PF) * SROW;
+    if ((ROWW * 4) % 128 == 0) {   // the row is staged: its global copy is dead (rows are 128-byte multiples at 256-byte aligned bases)
+      const char* dead = reinterpret_cast<const char*>(stash_b + (size_t)frame_t(i) * ROWW);
+      for (int u = lane; u < ROWW * 4 / 128; u += 32) wv_discard_l2_128(dead + (size_t)u * 128);
+    }
     const size_t ent0 = (size_t)(i & (L.RV - 1)) * LANES;
     const uint32_t* valw_row = sv.valw + ent0 * K;
     const int* vale_row = sv.vale + ent0;

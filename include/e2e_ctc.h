@@ -201,6 +201,19 @@ int e2e_ctc_viterbi_align_device(const e2e_ctc_desc* desc, int32_t is_ctc, const
                                  const void* targets, const void* logits_lengths, const void* targets_lengths,
                                  int64_t* aligned, void* workspace, size_t workspace_bytes, void* cuda_stream);
 
+/* ------------------------------------------------------------------- CTC without blank ----- */
+
+/* Loss and gradient of the blank-free CTC variant -- the reference's pytorch_end2end/functions/ctc_without_blank.py:
+ * _ctc_without_blank_loss (:13-88) under _ctc_without_blank_3d_loss (:91-117).  `log_probs` are log-probabilities
+ * [B,T,V]; space_idx = -1: the lattice is the target sequence itself; otherwise one optional `space_idx` cell is
+ * added at either end.  losses[b] = -log Z; grads[b,t,v] = exp(lp) - posterior for t < T_b and 0 past the
+ * utterance's frames; an utterance with no alignment gives +inf / NaN as in the reference.  fp64 log-space. */
+size_t e2e_ctc_noblank_workspace_bytes(const e2e_ctc_desc* desc);
+int e2e_ctc_noblank_fwd_bwd_device(const e2e_ctc_desc* desc, int32_t space_idx, const void* log_probs,
+                                   const void* targets, const void* logits_lengths, const void* targets_lengths,
+                                   void* losses, void* grads, void* workspace, size_t workspace_bytes,
+                                   void* cuda_stream);
+
 /* --------------------------------------------------------------- greedy decode, device ----- */
 
 size_t e2e_ctc_greedy_workspace_bytes(const e2e_ctc_desc* desc);
@@ -249,7 +262,7 @@ uint64_t e2e_ctc_launch_count(void);
  * bracketed by CUDA events on its launching stream.  e2e_ctc_profile_read() waits for the pending
  * events, then fills ms[k] (summed device milliseconds) and launches[k] per kernel kind
  * k = 0 row_stats, 1 lattice, 2 gradient, 3 loss_reduce, 4 argmax, 5 collapse, 6 scale_rows
- * (n_kinds >= 7),
+ * (n_kinds >= 9),
  * and clears the record.  All launches since the previous read must have been made on ONE device. */
 int e2e_ctc_profile_enable(int32_t on);
 int e2e_ctc_profile_read(double* ms, uint64_t* launches, int32_t n_kinds);

@@ -55,6 +55,9 @@ def lib():
         L.ctc_oracle_align.argtypes = [dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ip, ctypes.c_int, ip, ip,
                                        ctypes.c_int, ctypes.c_int, ip]
         L.ctc_oracle_align.restype = None
+        L.ctc_oracle_noblank.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.c_int, ctypes.c_int, ctypes.c_int, ip, ctypes.c_int,
+                                         ip, ip, ctypes.c_int, dp, dp]
+        L.ctc_oracle_noblank.restype = None
         _lib = L
     return _lib
 
@@ -241,3 +244,21 @@ def get_alignment_3d(log_probs, targets, logits_lengths, targets_lengths, is_ctc
     out = np.zeros((B, T), dtype=np.int64)
     lib().ctc_oracle_align(_dptr(lp), B, T, V, _iptr(tg), Lmax, _iptr(il), _iptr(tl), int(blank_idx), 1 if is_ctc else 0, _iptr(out))
     return torch.from_numpy(out)
+
+
+def ctc_without_blank(log_probs, targets, logits_lengths, targets_lengths, space_idx=-1):
+    """pytorch_end2end/functions/ctc_without_blank.py:91-117 through the C restatement: (losses [B] float64,
+    grads [B,T,V] float64; the reference casts both to float32)."""
+    lp = np.ascontiguousarray(log_probs.detach().to("cpu").to(torch.float32).numpy())
+    B, T, V = lp.shape
+    tg = np.ascontiguousarray(targets.to("cpu").to(torch.int64).numpy()).reshape(B, -1)
+    Lmax = tg.shape[1]
+    if Lmax == 0:
+        tg, Lmax = np.zeros((B, 1), dtype=np.int64), 1
+    il = np.ascontiguousarray(logits_lengths.to("cpu").to(torch.int64).numpy())
+    tl = np.ascontiguousarray(targets_lengths.to("cpu").to(torch.int64).numpy())
+    losses = np.zeros(B, dtype=np.float64)
+    grads = np.zeros((B, T, V), dtype=np.float64)
+    lib().ctc_oracle_noblank(lp.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), B, T, V, _iptr(tg), Lmax, _iptr(il), _iptr(tl),
+                             int(space_idx), _dptr(losses), _dptr(grads))
+    return torch.from_numpy(losses), torch.from_numpy(grads)

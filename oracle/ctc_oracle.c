@@ -23,6 +23,8 @@
  *                                                              maximal -- torch's rule) then
  *                                                              collapse repeats / drop blanks
  *   ctc_oracle_log_softmax_f32() <- pytorch_end2end/modules/ctc_loss.py:40 (F.log_softmax, fp32)
+ *   ctc_oracle_noblank()   <- pytorch_end2end/functions/ctc_without_blank.py:13-88 (_ctc_without_blank_loss) and
+ *                                                              :91-117 (batch driver); pinned by tests/golden/noblank_*.npz
  *   ctc_oracle_align()     <- pytorch_end2end/utils/alignment.py:50-106 (_get_alignment_ctc_1d), :9-47
  *                                                              (_get_alignment_asg_1d), :109-138 (batch driver,
  *                                                              -100 fill); pinned by tests/golden/align_*.npz,
@@ -251,5 +253,77 @@ void ctc_oracle_align(const double* lp, int B, int T, int V, const int64_t* targ
     int64_t* o = out + (size_t)b * T;
     for (int k = 0; k < T; k++) o[k] = -100;
     align_utterance(lp + (size_t)b * T * V, V, targets + (size_t)b * Lmax, (int)in_len[b], (int)tgt_len[b], blank, is_ctc, o);
+  }
+}
+
+/*
+ * CTC without blank, one utterance (ctc_without_blank.py:13-88).  lp: [T][V] log-probabilities widened to double,
+ * lp32: the same as float32 (the reference's np.exp(logits) runs in float32); grad: [T][V].  Returns -loss_forward.
+ */
+static double noblank_utterance(const double* lp, const float* lp32, int V, const int64_t* targets, int T, int L, int space,
+                                double* grad) {
+  int uas = 0, S;
+  int64_t* ext;
+  if (L == 0 || (L == 1 && targets[0] == space)) { S = 1; ext = (int64_t*)malloc(sizeof(int64_t)); ext[0] = space; }
+  else if (space == -1) { S = L; ext = (int64_t*)malloc(sizeof(int64_t) * (size_t)S); memcpy(ext, targets, sizeof(int64_t) * (size_t)S); }
+  else {
+    uas = 1; S = L + 2; ext = (int64_t*)malloc(sizeof(int64_t) * (size_t)S);
+    for (int j = 0; j < S; j++) ext[j] = space;
+    memcpy(ext + 1, targets, sizeof(int64_t) * (size_t)L);
+  }
+  for (int j = 0; j < S; j++) if (ext[j] < 0) ext[j] += V;               /* numpy's negative index */
+  double* alpha = (double*)malloc(sizeof(double) * (size_t)S * (size_t)T);
+  double* beta = (double*)malloc(sizeof(double) * (size_t)S * (size_t)T);
+  for (size_t q = 0; q < (size_t)S * (size_t)T; q++) { alpha[q] = NEG_INF; beta[q] = NEG_INF; }
+#define AL(j, t) alpha[(size_t)(j) * T + (t)]
+#define BE(j, t) beta[(size_t)(j) * T + (t)]
+#define LP(t, v) lp[(size_t)(t) * V + (v)]
+  if (T > 1 || S == 1) AL(0, 0) = LP(0, ext[0]);
+  if (S > 1 && uas) AL(1, 0) = LP(0, ext[1]);
+  for (int t = 1; t < T; t++) {
+    const int start = uas ? imax(0, S - T + t - 1) : imax(0, S - T + t);
+    const int end = uas ? imin(t + 2, S) : imin(t + 1, S);
+    for (int j = start; j < end; j++) AL(j, t) = AL(j, t - 1);
+    for (int j = start; j < end; j++) {
+      if (j > 0) AL(j, t) = lse2(AL(j, t), AL(j - 1, t - 1));
+      AL(j, t) += LP(t, ext[j]);
+    }
+  }
+  const double loss_forward = (S > 1 && uas) ? lse2(AL(S - 1, T - 1), AL(S - 2, T - 1)) : AL(S - 1, T - 1);
+  if (T > 1 || S == 1) BE(S - 1, T - 1) = 0.0;
+  if (S > 1 && uas) BE(S - 2, T - 1) = 0.0;
+  for (int t = T - 2; t >= 0; t--) {
+    const int start = uas ? imax(0, S - T + t - 1) : imax(0, S - T + t);
+    const int end = uas ? imin(t + 2, S) : imin(t + 1, S);
+    for (int j = start; j < end; j++) {
+      BE(j, t) = BE(j, t + 1) + LP(t + 1, ext[j]);
+      if (j < S - 1) BE(j, t) = lse2(BE(j, t), BE(j + 1, t + 1) + LP(t + 1, ext[j + 1]));
+    }
+  }
+  double* psum = (double*)malloc(sizeof(double) * (size_t)T * (size_t)V);
+  for (size_t q = 0; q < (size_t)T * (size_t)V; q++) psum[q] = NEG_INF;
+  for (int i = 0; i < S; i++)
+    for (int t = 0; t < T; t++) psum[(size_t)t * V + ext[i]] = lse2(psum[(size_t)t * V + ext[i]], AL(i, t) + BE(i, t));
+  for (size_t q = 0; q < (size_t)T * (size_t)V; q++) grad[q] = (double)expf(lp32[q]) - exp(psum[q] - loss_forward);
+#undef AL
+#undef BE
+#undef LP
+  free(ext); free(alpha); free(beta); free(psum);
+  return -loss_forward;
+}
+
+/* _ctc_without_blank_3d_loss (:91-117): grads zero past every utterance's frames. */
+void ctc_oracle_noblank(const float* lp32, int B, int T, int V, const int64_t* targets, int Lmax, const int64_t* in_len,
+                        const int64_t* tgt_len, int space, double* losses, double* grads) {
+#pragma omp parallel for schedule(dynamic)
+  for (int b = 0; b < B; b++) {
+    const int Ti = (int)in_len[b];
+    const float* x32 = lp32 + (size_t)b * T * V;
+    double* x = (double*)malloc(sizeof(double) * (size_t)Ti * (size_t)V);
+    for (size_t q = 0; q < (size_t)Ti * (size_t)V; q++) x[q] = (double)x32[q];
+    double* g = grads + (size_t)b * T * V;
+    for (size_t q = 0; q < (size_t)T * (size_t)V; q++) g[q] = 0.0;
+    losses[b] = noblank_utterance(x, x32, V, targets + (size_t)b * Lmax, Ti, (int)tgt_len[b], space, g);
+    free(x);
   }
 }

@@ -181,3 +181,24 @@ def test_alignment_oracle_matches_reference_goldens(name):
                                   torch.from_numpy(g["logits_lengths"]), torch.from_numpy(g["targets_lengths"]),
                                   is_ctc=bool(g["is_ctc"]))
     assert out.dtype == torch.int64 and torch.equal(out, torch.from_numpy(g["aligned"]))
+
+
+# --------------------------------------------------------------------------------------------
+# CTC without blank: the C restatement against the reference's own numba code
+# --------------------------------------------------------------------------------------------
+NOBLANK_GOLDENS = ["noblank_c1", "noblank_c1_space", "noblank_c2_b4", "noblank_c2_b4_space", "noblank_edge_space", "noblank_edge"]
+
+
+@pytest.mark.parametrize("name", NOBLANK_GOLDENS)
+def test_noblank_oracle_matches_reference_goldens(name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    losses, grads = oracle.ctc_without_blank(torch.from_numpy(g["log_probs"]), torch.from_numpy(g["targets"]),
+                                             torch.from_numpy(g["logits_lengths"]), torch.from_numpy(g["targets_lengths"]),
+                                             space_idx=int(g["space_idx"]))
+    rl, rg = torch.from_numpy(g["losses"]), torch.from_numpy(g["grads"]).double()
+    assert torch.equal(torch.isnan(grads), torch.isnan(rg)) and torch.equal(torch.isinf(losses), torch.isinf(rl))
+    fin = torch.isfinite(rl)
+    torch.testing.assert_close(losses[fin], rl[fin], rtol=1e-12, atol=1e-12)
+    ok = ~torch.isnan(rg)
+    # the reference's grads array has the dtype of its float32 input (np.zeros_like(logits)): one float32 rounding
+    torch.testing.assert_close(grads[ok], rg[ok], rtol=0, atol=2e-7)

@@ -3,7 +3,7 @@
 usage: ncu_lines.py export.csv [topN]"""
 import csv, sys, collections
 path = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-rows = list(csv.reader(open(path)))
+rows = list(csv.reader(open(path, errors="replace")))
 agg = collections.OrderedDict()
 cur_file = None; hdr = None; first_kernel_done = False; kernels = 0
 for r in rows:

@@ -10,7 +10,7 @@ from end2end_b200 import CTCDecoder, CTCLossEngine  # noqa: E402
 cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 B, T, V, Lmin, Lmax, seed, dtype, full = oracle.CONFIGS[cfg]
-if len(sys.argv) > 3:
+if len(sys.argv) > 3 and sys.argv[3].isdigit() and int(sys.argv[3]) > 0:
     B = int(sys.argv[3])
 x, tg, ll, tl = oracle.make_inputs(B, T, V, Lmin, Lmax, seed, dtype=dtype, full_length=full)
 eng = CTCLossEngine(0)
@@ -18,6 +18,15 @@ xg, tgc, llc, tlc = x.cuda(), tg.cuda(), ll.cuda(), tl.cuda()
 for _ in range(steps):
     losses, grads, red, _ = eng.step(xg, tgc, llc, tlc, True, 1.0 / B, 1.0 / B)
 if "--greedy" in sys.argv:
-    CTCDecoder(beam_width=1).decode(xg, llc)
+    for _ in range(2):
+        CTCDecoder(beam_width=1).decode(xg, llc)
+if "--scale" in sys.argv:        # an upstream gradient that is not 1: the in-place row scaling kernel does real work
+    for _ in range(2):
+        eng.scale_rows_(grads, torch.full((B,), 0.5, device="cuda", dtype=grads.dtype))
+if "--align" in sys.argv:
+    from end2end_b200.utils.alignment import get_alignment_3d_device
+    lp = torch.log_softmax(xg.float(), 2)
+    for _ in range(2):
+        get_alignment_3d_device(lp, tgc, llc, tlc)
 torch.cuda.synchronize()
 print(cfg, "loss", float(red))
