@@ -544,7 +544,7 @@ def run_ours(args, wl):
     # ---- strong scaling: c3 at its FIXED global batch, sharded over the ranks by plan_shards ----
     if not args.no_extras:
         sB = WORKLOADS["c3"][0]
-        sbk = Bucket("c3", dev, rank, world, max_rotate=16, global_batch=sB)
+        sbk = Bucket("c3", dev, rank, world, max_rotate=64, global_batch=sB)     # enough slots to stay in rotation mode at 8 ranks
         sres = measure_bucket(sbk, dev, world, 20, 3, barrier, flush_buf, with_autograd=False, profile_steps=0)
         s_ms = max_over_ranks(sres["ms"]) / 20
         extras["strong"] = {"workload": "c3: " + WORKLOADS["c3"][8], "global_batch": sB, "bucket_sizes": [len(b) for b in sbk.buckets],
@@ -694,10 +694,13 @@ def run_ours(args, wl):
             "cpu_baseline": cpu_baseline,
         }
         line.update(extras)
-        print(json.dumps(line))
+        out_line = json.dumps(line)
+    else:
+        out_line = None
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
+    return out_line
 
 
 def main():
@@ -727,7 +730,19 @@ def main():
             run_reference(args, args.workload)
     else:
         os.environ.setdefault("OMP_NUM_THREADS", "1")     # our arm's host side is single-threaded issue work
-        run_ours(args, args.workload)
+        # ONE JSON line on stdout, whatever the libraries underneath print (NCCL writes its version banner to stdout):
+        # everything else this process writes to fd 1 goes to stderr, the line itself to the real stdout
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            line = run_ours(args, args.workload)
+        finally:
+            sys.stdout.flush()
+            os.dup2(real_stdout, 1)
+            os.close(real_stdout)
+        if line is not None:
+            print(line, flush=True)
 
 
 if __name__ == "__main__":

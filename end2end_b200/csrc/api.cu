@@ -369,6 +369,11 @@ bool make_loss_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   if (gather && d.batch <= 256 && make_fused_plan(d, fused, p)) return true;
   if (make_wave_plan(d, fused, p)) return true;
   memset(p, 0, sizeof(*p));
+  // short lattices the wave kernel does not take (one lattice warp per sweep but more than 74 utterances) while every
+  // cluster still has an SM pair's worth of room: the general kernel's helper warps beat the two-warp sweep CTA
+  // (c3-shaped bucket of 128 utterances, one rank of an 8-GPU job: 103 us against 131 us)
+  if (!gather && d.batch <= 148 && make_fused_plan(d, fused, p)) return true;
+  memset(p, 0, sizeof(*p));
   if (make_sweep_plan(d, fused, p)) return true;
   memset(p, 0, sizeof(*p));
   return make_fused_plan(d, fused, p);

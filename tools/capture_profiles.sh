@@ -41,11 +41,13 @@ if [ "$what" = "san" ] || [ "$what" = "all" ]; then
     timeout 600 compute-sanitizer --tool $tool --print-limit 20 "$@" > $out/san_${tool}_$name.log 2>&1
     tail -3 $out/san_${tool}_$name.log
   }
-  for tool in memcheck racecheck synccheck; do
+  san memcheck wave_c2 python tools/run_one.py c2 1 2
+  san memcheck wave_c1 python tools/run_one.py c1 1
+  san memcheck sweep_c3 python tools/run_one.py c3 1 160
+  san memcheck general_c4_greedy_align python tools/run_one.py c4 1 3 --greedy --align
+  for tool in racecheck synccheck; do
     san $tool wave_c2 python tools/run_one.py c2 1 2
-    san $tool wave_c1 python tools/run_one.py c1 1
-    san $tool sweep_c3 python tools/run_one.py c3 1 160
-    san $tool general_c4 python tools/run_one.py c4 1 3 --greedy --align
+    san $tool general_c4_greedy_align python tools/run_one.py c4 1 3 --greedy --align
   done
 fi
 ls -la $out
