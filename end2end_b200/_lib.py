@@ -28,6 +28,7 @@ EXPORTS = (
     "e2e_ctc_graph_create", "e2e_ctc_graph_launch", "e2e_ctc_graph_destroy",
     "e2e_ctc_viterbi_workspace_bytes", "e2e_ctc_viterbi_align_device",
     "e2e_ctc_noblank_workspace_bytes", "e2e_ctc_noblank_fwd_bwd_device",
+    "e2e_ctc_host_alloc", "e2e_ctc_host_free",
 )
 KERNEL_KINDS = ("row_stats", "lattice", "gradient", "loss_reduce", "argmax", "collapse", "scale_rows", "viterbi", "ctc_without_blank")
 
@@ -110,6 +111,10 @@ def load():
     L.e2e_ctc_noblank_workspace_bytes.restype = sz
     L.e2e_ctc_noblank_fwd_bwd_device.argtypes = [dp, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     L.e2e_ctc_noblank_fwd_bwd_device.restype = ctypes.c_int
+    L.e2e_ctc_host_alloc.argtypes = [sz, ctypes.POINTER(vp)]
+    L.e2e_ctc_host_alloc.restype = ctypes.c_int
+    L.e2e_ctc_host_free.argtypes = [vp]
+    L.e2e_ctc_host_free.restype = ctypes.c_int
     L.e2e_ctc_graph_launch.argtypes = [vp, vp]
     L.e2e_ctc_graph_destroy.argtypes = [vp]
     L.e2e_ctc_graph_destroy.restype = None

@@ -613,6 +613,22 @@ int e2e_ctc_greedy_decode_device(const e2e_ctc_desc* desc, const void* logits, c
                        reinterpret_cast<char*>(workspace), reinterpret_cast<cudaStream_t>(cuda_stream));
 }
 
+// ---- pinned host memory for result buffers -------------------------------------------------------
+// The host-buffer entry points write their results straight into PINNED caller buffers (see e2e_ctc_engine_loss_host);
+// a binding that has no pinned allocator of its own takes its result buffers from here.
+int e2e_ctc_host_alloc(size_t bytes, void** out) {
+  if (!out || bytes == 0) { set_error("host_alloc: bad arguments"); return E2E_ERR_INVALID_ARGUMENT; }
+  *out = nullptr;
+  E2E_CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+  return E2E_OK;
+}
+
+int e2e_ctc_host_free(void* p) {
+  if (!p) return E2E_OK;
+  E2E_CUDA_TRY(cudaFreeHost(p));
+  return E2E_OK;
+}
+
 // ---- Viterbi forced alignment -------------------------------------------------------
 size_t e2e_ctc_viterbi_workspace_bytes(const e2e_ctc_desc* desc, int32_t is_ctc) {
   if (check_desc(desc, true) != E2E_OK) return 0;

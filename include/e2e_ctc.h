@@ -249,6 +249,11 @@ int e2e_ctc_engine_greedy_host(e2e_ctc_engine* engine, const e2e_ctc_desc* desc,
                                const void* logits_lengths, int64_t* decoded,
                                int64_t* decoded_lengths);
 
+/* Pinned (page-locked, device-addressable) host memory for result buffers: when `losses` / `grads` of
+ * e2e_ctc_engine_loss_host live in such memory the kernels store into them directly and no copy-out stage runs. */
+int e2e_ctc_host_alloc(size_t bytes, void** out);
+int e2e_ctc_host_free(void* p);
+
 /* Bytes moved by the last engine call (for benchmarks): host->device and device->host.  Every byte that crosses
  * PCIe is counted, whether the copy engine moved it or -- result buffers in pinned host memory -- the kernels
  * stored it into the caller's buffer directly. */
