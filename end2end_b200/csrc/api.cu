@@ -122,7 +122,7 @@ static bool make_sweep_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   const int rowlen = p->dense ? d.alphabet : d.max_targets + 1;
   p->post_stride = p->cells / 2 + 4;
   p->vpad = p->dense ? ((d.alphabet + 1 + 3) & ~3) : 0;
-  const int H = K / 2, PF = K >= 24 ? 2 : 8;
+  const int H = K / 2, PF = K >= 24 ? 2 : kSweepPFSmall;
   const int et = f64 ? 8 : 4;
   const int esz = f64 ? 8 : (d.dtype == E2E_F32 ? 4 : 2);
   SweepLayout L;
@@ -149,7 +149,11 @@ static bool make_sweep_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   int cf = 32;
   // several CTAs per SM when the batch is large; otherwise whatever fits
   static const int want_kb = env_int("E2E_CTC_SWEEP_SMEM_KB", 0);   // experiments only
-  const size_t want = want_kb > 0 ? (size_t)want_kb * 1024 : (d.batch > 148 ? 56 * 1024 : 200 * 1024);
+  // more than four CTAs per SM's worth of utterances (4 x 148): seven CTAs per SM (<= 32 KB each, 128 registers: the
+  // whole batch in ONE wave) beat four with longer emission chunks -- c3 (B=1024): 267 -> 229 us; up to 592 utterances
+  // four CTAs per SM already hold the batch and the 32-frame chunks win (B=512: 140 us)
+  const size_t want = want_kb > 0 ? (size_t)want_kb * 1024
+                                  : (d.batch > 4 * 148 ? 32 * 1024 : (d.batch > 148 ? 56 * 1024 : 200 * 1024));
   while (cf > 8 && layout(cf) > want) cf >>= 1;
   const size_t smem = layout(cf);
   if (smem > 220 * 1024) return false;

@@ -25,6 +25,16 @@ struct SweepLayout {
   int off_lab, off_warp, warp_bytes, w_E, w_raw, w_stat, w_rs, w_acc, w_stage;
 };
 
+// sweep kernel, narrow variants (K < 24 cells per lane): stashed rows each warp keeps in flight, and the resident CTAs
+// per SM the register allocation aims at (-D overrides are for experiments)
+#ifndef E2E_SWEEP_PF_SMALL
+#define E2E_SWEEP_PF_SMALL 4
+#endif
+#ifndef E2E_SWEEP_MINBLK
+#define E2E_SWEEP_MINBLK 7
+#endif
+constexpr int kSweepPFSmall = E2E_SWEEP_PF_SMALL;
+
 constexpr int kWaveCF = 8;       // wave kernel: frames per hand-off chunk
 constexpr int kWaveRB = 32;      // boundary-slot ring depth (frames)
 constexpr int kWavePF = 4;       // stashed rows each combiner warp keeps in flight

@@ -80,7 +80,7 @@ template <int K> struct SweepCfg {
   static constexpr int H = K / 2;
   static constexpr int WORDS = (K + 1 + 3) & ~3;
   static constexpr int ROWW = 32 * WORDS;
-  static constexpr int PF = K >= 24 ? 2 : 8;
+  static constexpr int PF = K >= 24 ? 2 : kSweepPFSmall;
 };
 
 template <int K, typename ET>
@@ -576,7 +576,7 @@ __device__ void run_sweep(const SweepParams& p, unsigned char* smem, int b, int 
 
 // ---- kernel -----------------------------------------------------------------------------------
 template <int K, bool F64>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(64, K <= 8 ? E2E_SWEEP_MINBLK : 1)
 ctc_sweep_kernel(const SweepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using ET = typename std::conditional<F64, double, float>::type;
