@@ -153,7 +153,7 @@ static bool make_sweep_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   // whole batch in ONE wave) beat four with longer emission chunks -- c3 (B=1024): 267 -> 229 us; up to 592 utterances
   // four CTAs per SM already hold the batch and the 32-frame chunks win (B=512: 140 us)
   const size_t want = want_kb > 0 ? (size_t)want_kb * 1024
-                                  : (d.batch > 4 * 148 ? 32 * 1024 : (d.batch > 148 ? 56 * 1024 : 200 * 1024));
+                                  : (d.batch > 4 * 148 && K <= 8 ? 32 * 1024 : (d.batch > 148 ? 56 * 1024 : 200 * 1024));   // wide variants are register-bound at four CTAs per SM
   while (cf > 8 && layout(cf) > want) cf >>= 1;
   const size_t smem = layout(cf);
   if (smem > 220 * 1024) return false;
