@@ -357,7 +357,7 @@ static bool make_fused_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
 
 
 // Which lattice kernel runs a shape (all three are parity-tested against the oracle on the shapes they take):
-//  * wave kernel: latency shapes (B <= 148 utterances, small alphabet, <= 255 labels) -- four lattice warps per sweep;
+//  * wave kernel: latency shapes (B <= 148 utterances, small alphabet, 64..255 labels) -- two to four lattice warps per sweep;
 //  * one-warp-per-sweep kernel: throughput shapes with small alphabets (many utterances per SM);
 //  * general kernel: everything else -- large alphabets (gather mode), and a single label symbol (V == 2, where the
 //    sweep kernel's lane-exponent rule loses the only feasible path of a tight alignment under very peaky
@@ -371,12 +371,12 @@ bool make_loss_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   if (force == kPlanSweep && make_sweep_plan(d, fused, p)) return true;
   if (d.alphabet == 2) return make_fused_plan(d, fused, p);
   if (gather && d.batch <= 256 && make_fused_plan(d, fused, p)) return true;
-  if (make_wave_plan(d, fused, p)) return true;
+  // short lattices (<= 128 cells: one lattice warp per sweep either way) in batches that leave every cluster an SM
+  // pair's worth of room: the general kernel beats both the wave kernel (c1: 24.0 against 27.5 us) and the two-warp
+  // sweep CTA (a c3-shaped bucket of 128 utterances, one rank of an 8-GPU job: 103 against 131 us)
+  if (!gather && 2 * d.max_targets + 1 <= 128 && d.batch <= 148 && make_fused_plan(d, fused, p)) return true;
   memset(p, 0, sizeof(*p));
-  // short lattices the wave kernel does not take (one lattice warp per sweep but more than 74 utterances) while every
-  // cluster still has an SM pair's worth of room: the general kernel's helper warps beat the two-warp sweep CTA
-  // (c3-shaped bucket of 128 utterances, one rank of an 8-GPU job: 103 us against 131 us)
-  if (!gather && d.batch <= 148 && make_fused_plan(d, fused, p)) return true;
+  if (make_wave_plan(d, fused, p)) return true;
   memset(p, 0, sizeof(*p));
   if (make_sweep_plan(d, fused, p)) return true;
   memset(p, 0, sizeof(*p));
