@@ -274,7 +274,7 @@ static bool make_fused_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   L.gather = dense ? 0 : 1;
   L.dbg = tn.dbg;
   const bool heavy_rows = !dense || V > 32;   // producer work per frame: a whole row of > 32 symbols, or a gather
-  const int maxw = NB <= 4 ? 8 : 5;
+  const int maxw = NB <= 4 ? 8 : 5;   // (six or eight combiner warps measured no better than four)
   const int nsc = NB <= 4 ? 1 : 0;              // scaler warp (exponent snapshots): every class but the large-lattice one
   if (NB == 10) { L.NP = 1; L.NC = 3; L.nwarps = 5; }
   else if (latency) { L.NP = 2; L.NC = 4; L.nwarps = 8; }
@@ -301,6 +301,7 @@ static bool make_fused_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   if ((size_t)4 * L.PB * L.es * 8 <= (size_t)(dense ? 32 : 48) * 1024) L.R = 4 * L.PB;
   while (L.R < 128 && (size_t)2 * L.R * L.es * 8 <= (size_t)(latency ? 48 : 24) * 1024) L.R *= 2;
   if (tn.r >= 2 * L.PB && !(tn.r & (tn.r - 1))) L.R = tn.r;
+  if (dense && d.dtype != E2E_F64 && V <= 32 && L.R < 64) L.R = 64;   // the lane-per-frame row producer (<= 32 symbols) works in passes of 32 frames: two in the ring
   if (L.R > 16 * L.PB) L.R = 16 * L.PB;   // at most 16 emission blocks (one mbarrier each)
   if (L.RV > 32) L.RV = 32;
   auto ilog2 = [](int v) { int k = 0; while ((1 << k) < v) k++; return k; };
@@ -357,7 +358,7 @@ static bool make_fused_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
 
 
 // Which lattice kernel runs a shape (all three are parity-tested against the oracle on the shapes they take):
-//  * wave kernel: latency shapes (B <= 148 utterances, small alphabet, 64..255 labels) -- two to four lattice warps per sweep;
+//  * wave kernel: latency shapes (B <= 148 utterances, small alphabet, 128..255 labels) -- four lattice warps per sweep;
 //  * one-warp-per-sweep kernel: throughput shapes with small alphabets (many utterances per SM);
 //  * general kernel: everything else -- large alphabets (gather mode), and a single label symbol (V == 2, where the
 //    sweep kernel's lane-exponent rule loses the only feasible path of a tight alignment under very peaky
@@ -371,10 +372,12 @@ bool make_loss_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   if (force == kPlanSweep && make_sweep_plan(d, fused, p)) return true;
   if (d.alphabet == 2) return make_fused_plan(d, fused, p);
   if (gather && d.batch <= 256 && make_fused_plan(d, fused, p)) return true;
-  // short lattices (<= 128 cells: one lattice warp per sweep either way) in batches that leave every cluster an SM
-  // pair's worth of room: the general kernel beats both the wave kernel (c1: 24.0 against 27.5 us) and the two-warp
-  // sweep CTA (a c3-shaped bucket of 128 utterances, one rank of an 8-GPU job: 103 against 131 us)
-  if (!gather && 2 * d.max_targets + 1 <= 128 && d.batch <= 148 && make_fused_plan(d, fused, p)) return true;
+  // lattices of <= 256 cells (the wave kernel would run them on one or two lattice warps with its small helper set) in
+  // batches that leave every cluster an SM pair's worth of room: the general kernel beats both the wave kernel (c1: 24.0
+  // against 27.5 us; B=64, T=400, <= 63 / 95 / 127 labels: 94 / 115 / 113 against 138 / 152 / 151 us) and the two-warp sweep
+  // CTA (a c3-shaped bucket of 128 utterances, one rank of an 8-GPU job: 103 against 131 us).  From 128 labels on the wave
+  // kernel's four lattice warps win (113 against 138 us).
+  if (!gather && 2 * d.max_targets + 1 <= 256 && d.batch <= 148 && make_fused_plan(d, fused, p)) return true;
   memset(p, 0, sizeof(*p));
   if (make_wave_plan(d, fused, p)) return true;
   memset(p, 0, sizeof(*p));

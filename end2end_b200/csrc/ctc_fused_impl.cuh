@@ -186,6 +186,57 @@ __device__ __forceinline__ float fz_load_logit(const void* base, int dtype, long
   return dtype == E2E_BF16 ? __uint_as_float((uint32_t)r << 16) : __half2float(__ushort_as_half(r));
 }
 
+// dense mode, alphabets of <= 32 symbols (32 / 16-bit logits): ONE LANE PER FRAME over passes of 32 frames.  A lane loads
+// its whole row into registers (all loads independent and in flight together), reduces it serially -- no cross-lane
+// shuffles -- and writes the row's emissions; the HBM round trip (~2000 cycles) is paid once
+// per 32 frames instead of once per four (the warp-per-frame version cost 775 cycles per frame per producer, and the
+// lattice warp waited for emissions 27 % of its time).  A pass covers 32 / PB emission blocks; each is published on its
+// own mbarrier.  The ring must hold two passes (R >= 64).
+__device__ __noinline__ double fz_produce_lanes(const FzParams& p, const FzView& sv, long long xbase, int Ti, int i0, int lane, bool BWD) {
+  const FzLayout& L = p.L;
+  const int i = i0 + lane;
+  if (i >= Ti) return 0.0;
+  const long long ro = xbase + (long long)(BWD ? (Ti - 1 - i) : i) * p.st;
+  double* Erow = sv.E + (size_t)(i & (L.R - 1)) * L.es;
+  const int V = p.V;
+  float m = -INFINITY, s = 0.f;
+  bool nan = false;
+  float xv[32];
+#pragma unroll
+  for (int v = 0; v < 32; v++) xv[v] = v < V ? fz_load_logit(p.logits, p.dtype, ro + v) : -INFINITY;
+#pragma unroll
+  for (int v = 0; v < 32; v++) { nan |= xv[v] != xv[v]; m = fmaxf(m, xv[v]); }
+#pragma unroll
+  for (int v = 0; v < 32; v++) s += expf(xv[v] - m);   // exp(-inf) = 0 for the padding columns
+  float ls = logf(s);
+  if (nan) { m = NAN; ls = NAN; }                       // a NaN in the row poisons it, as in torch's log_softmax
+#pragma unroll
+  for (int v = 0; v < 32; v++) if (v < V) Erow[v] = fz_emission(xv[v], m, ls, p.from_logits);
+  const double mls = (double)m + (double)ls;
+  Erow[V] = 0.0;                                       // the column padding cells read
+  Erow[V + 1] = p.from_logits ? 1.0 : exp(mls);        // turns the emission back into exp(x)
+  return mls;
+}
+
+__device__ __forceinline__ double fz_producer_dense(const FzParams& p, const FzView& sv, int b, int Ti, int pw, int lane, bool BWD) {
+  constexpr int PASS = 32;
+  const FzLayout& L = p.L;
+  const int npass = (Ti + PASS - 1) / PASS, per = PASS / L.PB;
+  const long long xbase = (long long)b * p.sb;
+  double lse = 0.0;
+  for (int ps = pw; ps < npass; ps += L.NP) {
+    const int i0 = ps * PASS;
+    const int need = i0 + PASS - L.R;   // frames below `need` must have left the ring (write-after-read: plain progress words)
+    if (need > 0) {
+      while (sv.ctl->lat_prog < need || fz_min_done(sv.ctl->comb_done, L.NC) < need) { if (L.nap) __nanosleep(L.nap); }
+    }
+    lse += fz_produce_lanes(p, sv, xbase, Ti, i0, lane, BWD);
+    __syncwarp();
+    if (lane < per && i0 + lane * L.PB < Ti) fz_mbar_arrive(&sv.ctl->fullE[(ps * per + lane) & L.neb_mask]);
+  }
+  return warp_sum(lse);   // fixed order: deterministic loss for log-prob input
+}
+
 // dense mode: one WARP per frame, lanes over the symbols (coalesced row loads, warp-shuffle max / sum), four frames
 // per iteration so that the shuffle chains of independent rows overlap; the next group's loads are issued before
 // this group is reduced (HBM latency off the chain).  Deliberately a ROLLED loop in a separate function: the SM's
@@ -342,6 +393,12 @@ __device__ void fz_producer(const FzParams& p, const FzView& sv, int b, int Ti, 
   const int nblocks = (Ti + PB - 1) / PB;
   const long long xbase = (long long)b * p.sb;
   double lse = 0.0;
+  if (!GATHER && p.dtype != E2E_F64 && p.V <= 32) {
+    // alphabets of <= 32 symbols, 32 / 16-bit logits: the lane-per-frame row producer (its own pass loop)
+    lse = fz_producer_dense(p, sv, b, Ti, pw, lane, BWD);
+    if (lane == 0) sv.ctl->lse[pw] = lse;
+    return;
+  }
   long long dbg_wait = 0, dbg_work = 0;
   for (int bi = pw; bi < nblocks; bi += L.NP) {
     const int need = bi * PB + PB - L.R;   // frames below `need` must have left the ring
@@ -353,10 +410,9 @@ __device__ void fz_producer(const FzParams& p, const FzView& sv, int b, int Ti, 
     const long long dbg_b = FZ_CLK();
     if (GATHER) lse += fz_produce_gather(p, sv, b, xbase, Ti, Li, bi * PB, lane, BWD);
     else if (p.dtype == E2E_F64) lse += fz_produce_dense_f64(p, sv, xbase, Ti, bi * PB, lane, BWD);
-    else {
+    else {   // 33 .. 128 symbols: one warp per frame (a lane-per-frame pass over rows this long thrashes L1: 176 against 103 us on a c3 bucket)
       const int i0 = bi * PB, i1 = min(i0 + PB, Ti);
-      if (p.V <= 32) lse += fz_produce_dense<1>(p.logits, p.dtype, p.st, p.V, p.from_logits, sv.E, L.R - 1, L.es, xbase, Ti, i0, i1, lane, BWD);
-      else if (p.V <= 64) lse += fz_produce_dense<2>(p.logits, p.dtype, p.st, p.V, p.from_logits, sv.E, L.R - 1, L.es, xbase, Ti, i0, i1, lane, BWD);
+      if (p.V <= 64) lse += fz_produce_dense<2>(p.logits, p.dtype, p.st, p.V, p.from_logits, sv.E, L.R - 1, L.es, xbase, Ti, i0, i1, lane, BWD);
       else lse += fz_produce_dense<4>(p.logits, p.dtype, p.st, p.V, p.from_logits, sv.E, L.R - 1, L.es, xbase, Ti, i0, i1, lane, BWD);
     }
     __syncwarp();

@@ -1,4 +1,4 @@
-"""Step time of one workload through engine.step (kernel-level experiments): python tools/step_time.py cfg [batch] [reps]"""
+"""Step time of one workload through engine.step (kernel-level experiments): python tools/step_time.py cfg [batch] [reps] [Lmin Lmax]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, oracle
@@ -7,6 +7,8 @@ cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
 B, T, V, Lmin, Lmax, seed, dtype, full = oracle.CONFIGS[cfg]
 if len(sys.argv) > 2 and int(sys.argv[2]) > 0: B = int(sys.argv[2])
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+if len(sys.argv) > 5:       # override the target-length range (dispatch experiments)
+    Lmin, Lmax = int(sys.argv[4]), int(sys.argv[5])
 x, tg, ll, tl = oracle.make_inputs(B, T, V, Lmin, Lmax, seed, dtype=dtype, full_length=full)
 if os.environ.get("FORCE"): _lib.force_kernel(int(os.environ["FORCE"]))
 eng = CTCLossEngine(0)
