@@ -34,6 +34,27 @@ if [ "$what" = "ncu" ] || [ "$what" = "all" ]; then
   cap ncu_collapse_c4  ctc_collapse_kernel  1 python tools/run_one.py c4 2 0 --greedy
   cap ncu_scale_c2     ctc_scale_rows       1 python tools/run_one.py c2 2 0 --scale
   cap ncu_viterbi_c2   ctc_viterbi_kernel   1 python tools/run_one.py c2 2 0 --align
+  cap ncu_noblank_c2   ctc_noblank_kernel   1 python tools/run_one.py c2 2 0 --noblank
+  cap ncu_general_c1   ctc_fused_kernel     2 python tools/run_one.py c1 4
+fi
+if [ "$what" = "refresh" ]; then      # kernels changed after the first capture of the round
+  NCUO=$NCU
+  cap() {
+    local name=$1 regex=$2 skip=$3; shift 3
+    $NCUO --set full --import-source on -k "regex:$regex" -s $skip -c 1 -f -o $out/$name "$@" > $out/$name.log 2>&1
+    if [ -f $out/$name.ncu-rep ]; then
+      ncu -i $out/$name.ncu-rep --page raw --csv > $out/$name.raw.csv 2>/dev/null
+      ncu -i $out/$name.ncu-rep --page source --csv --print-source cuda,sass > $out/$name.source.csv 2>/dev/null
+      python tools/ncu_summary.py $out/$name.raw.csv > $out/$name.summary.txt 2>&1
+      python tools/ncu_lines.py $out/$name.source.csv 30 > $out/$name.lines.txt 2>&1
+      rm -f $out/$name.source.csv $out/$name.ncu-rep $out/$name.raw.csv
+    fi
+  }
+  cap ncu_sweep_c3     ctc_sweep_kernel     2 python tools/run_one.py c3 4
+  cap ncu_viterbi_c2   ctc_viterbi_kernel   1 python tools/run_one.py c2 2 0 --align
+  cap ncu_noblank_c2   ctc_noblank_kernel   1 python tools/run_one.py c2 2 0 --noblank
+  cap ncu_general_c1   ctc_fused_kernel     2 python tools/run_one.py c1 4
+  cap ncu_general_c4   ctc_fused_kernel     2 python tools/run_one.py c4 4
 fi
 if [ "$what" = "san" ] || [ "$what" = "all" ]; then
   san() {  # tool, name, command...

@@ -23,6 +23,10 @@ if "--greedy" in sys.argv:
 if "--scale" in sys.argv:        # an upstream gradient that is not 1: the in-place row scaling kernel does real work
     for _ in range(2):
         eng.scale_rows_(grads, torch.full((B,), 0.5, device="cuda", dtype=grads.dtype))
+if "--noblank" in sys.argv:
+    from end2end_b200.functions.ctc_without_blank import ctc_without_blank_3d_loss
+    for _ in range(2):
+        ctc_without_blank_3d_loss(torch.log_softmax(xg.float(), 2), tgc, llc, tlc)
 if "--align" in sys.argv:
     from end2end_b200.utils.alignment import get_alignment_3d_device
     lp = torch.log_softmax(xg.float(), 2)
