@@ -176,26 +176,45 @@ __device__ __forceinline__ double convert_chunk(const SweepParams& p, const Chun
       const char* rowp = lbase + (long long)t * p.st * esz;
       const int shift = (int)((reinterpret_cast<uintptr_t>(rowp) & 3) >> 1);      // 16-bit types: first element's halfword
       const uint32_t* wr = reinterpret_cast<const uint32_t*>(rslot);
-      auto elem = [&](int v) -> float {
-        if (p.dtype == E2E_F32) return __uint_as_float(wr[v]);
-        const int hw = shift + v;
-        return sw_half_to_float(wr[hw >> 1], p.dtype, (hw & 1) != 0);
-      };
+      float* Ef = reinterpret_cast<float*>(Erow);
+      const bool f32 = p.dtype == E2E_F32;
       // One lane walks a whole row: four independent max / sum chains (the serial one was latency-bound: a chunk of
       // 32 frames x 96 symbols took ~23k cycles, a third of BASELINE config 3's step).  The sum keeps a FIXED order
       // -- four strided partial sums, then (s0 + s1) + (s2 + s3) -- so results stay bitwise reproducible.
       float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY; bool nan = false;
       const int V4 = p.V & ~3;
-      for (int v = 0; v < V4; v += 4) {
-        const float x0 = elem(v), x1 = elem(v + 1), x2 = elem(v + 2), x3 = elem(v + 3);
-        nan |= (x0 != x0) | (x1 != x1) | (x2 != x2) | (x3 != x3);
-        m0 = x0 > m0 ? x0 : m0; m1 = x1 > m1 ? x1 : m1; m2 = x2 > m2 ? x2 : m2; m3 = x3 > m3 ? x3 : m3;
+      if (f32) {
+        for (int v = 0; v < V4; v += 4) {
+          const float x0 = __uint_as_float(wr[v]), x1 = __uint_as_float(wr[v + 1]), x2 = __uint_as_float(wr[v + 2]), x3 = __uint_as_float(wr[v + 3]);
+          nan |= (x0 != x0) | (x1 != x1) | (x2 != x2) | (x3 != x3);
+          m0 = x0 > m0 ? x0 : m0; m1 = x1 > m1 ? x1 : m1; m2 = x2 > m2 ? x2 : m2; m3 = x3 > m3 ? x3 : m3;
+        }
+        for (int v = V4; v < p.V; ++v) { const float x = __uint_as_float(wr[v]); nan |= x != x; m0 = x > m0 ? x : m0; }
+      } else {
+        // 16-bit logits: unpack WORD by word (two symbols per 32-bit load, two instructions per symbol) into the emission
+        // row as floats; the exp pass below reads them back.  (Unpacking symbol by symbol, twice, was half of all the
+        // instructions BASELINE config 3 executed.)  Symbol v sits in halfword shift + v of the staged row.
+        const int nw = (shift + p.V + 1) >> 1;
+        const bool bf = p.dtype == E2E_BF16;
+        for (int k = 0; k < nw; k += 2) {
+          const uint32_t w0 = wr[k], w1 = k + 1 < nw ? wr[k + 1] : 0u;
+          float a0, a1, a2, a3;
+          if (bf) { a0 = __uint_as_float(w0 << 16); a1 = __uint_as_float(w0 & 0xffff0000u); a2 = __uint_as_float(w1 << 16); a3 = __uint_as_float(w1 & 0xffff0000u); }
+          else {
+            const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&w0)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&w1));
+            a0 = f0.x; a1 = f0.y; a2 = f1.x; a3 = f1.y;
+          }
+          const int v0 = 2 * k - shift;
+          if (v0 >= 0 && v0 < p.V) { Ef[v0] = a0; nan |= a0 != a0; m0 = a0 > m0 ? a0 : m0; }
+          if (v0 + 1 < p.V) { Ef[v0 + 1] = a1; nan |= a1 != a1; m1 = a1 > m1 ? a1 : m1; }
+          if (v0 + 2 < p.V) { Ef[v0 + 2] = a2; nan |= a2 != a2; m2 = a2 > m2 ? a2 : m2; }
+          if (v0 + 3 < p.V) { Ef[v0 + 3] = a3; nan |= a3 != a3; m3 = a3 > m3 ? a3 : m3; }
+        }
       }
-      for (int v = V4; v < p.V; ++v) { const float x = elem(v); nan |= x != x; m0 = x > m0 ? x : m0; }
+      auto elem = [&](int v) -> float { return f32 ? __uint_as_float(wr[v]) : Ef[v]; };
       const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       // exp(x - max) once per symbol: kept in the emission row, normalised below
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      float* Ef = reinterpret_cast<float*>(Erow);
       for (int v = 0; v < V4; v += 4) {
         const float e0 = expf(elem(v) - m), e1 = expf(elem(v + 1) - m), e2 = expf(elem(v + 2) - m), e3 = expf(elem(v + 3) - m);
         Ef[v] = e0; Ef[v + 1] = e1; Ef[v + 2] = e2; Ef[v + 3] = e3;
