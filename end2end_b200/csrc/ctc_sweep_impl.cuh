@@ -155,8 +155,14 @@ __device__ __forceinline__ double convert_chunk(const SweepParams& p, const Chun
   const int i0 = c * p.cf;
   const int nf = min(p.cf, Ti - i0);
   double lse_part = 0.0;
-  if (lane >= nf) return lse_part;
-  const int f = lane;
+  // Dense 32/16-bit rows: a chunk of cf < 32 frames would leave lanes idle, so 32 / cf lanes SHARE a frame, each taking a
+  // contiguous range of the symbols (max and sum are combined with shuffles in a fixed order).  Other modes: one lane per frame.
+  const bool split = p.dense && !F64 && p.cf < 32;
+  const int lpf = split ? 32 / p.cf : 1;
+  const int f = split ? (lane & (p.cf - 1)) : lane;
+  const int sub = split ? lane / p.cf : 0;
+  if (f >= nf) return lse_part;
+  const unsigned grp = __activemask();   // every lane of a frame's group takes the same branches
   const int t = BWD ? (Ti - 1 - (i0 + f)) : (i0 + f);
   const int esz = F64 ? 8 : (p.dtype == E2E_F32 ? 4 : 2);
   const unsigned char* rslot = cx.raw + (size_t)f * p.rawrow;
@@ -182,21 +188,23 @@ __device__ __forceinline__ double convert_chunk(const SweepParams& p, const Chun
       // 32 frames x 96 symbols took ~23k cycles, a third of BASELINE config 3's step).  The sum keeps a FIXED order
       // -- four strided partial sums, then (s0 + s1) + (s2 + s3) -- so results stay bitwise reproducible.
       float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY; bool nan = false;
-      const int V4 = p.V & ~3;
+      // this lane's symbols [va, vb): the whole row, or its share of it (boundaries at multiples of four)
+      const int va = sub == 0 ? 0 : ((p.V * sub / lpf) & ~3), vb = sub + 1 == lpf ? p.V : ((p.V * (sub + 1) / lpf) & ~3);
+      const int V4 = va + ((vb - va) & ~3);
       if (f32) {
-        for (int v = 0; v < V4; v += 4) {
+        for (int v = va; v < V4; v += 4) {
           const float x0 = __uint_as_float(wr[v]), x1 = __uint_as_float(wr[v + 1]), x2 = __uint_as_float(wr[v + 2]), x3 = __uint_as_float(wr[v + 3]);
           nan |= (x0 != x0) | (x1 != x1) | (x2 != x2) | (x3 != x3);
           m0 = x0 > m0 ? x0 : m0; m1 = x1 > m1 ? x1 : m1; m2 = x2 > m2 ? x2 : m2; m3 = x3 > m3 ? x3 : m3;
         }
-        for (int v = V4; v < p.V; ++v) { const float x = __uint_as_float(wr[v]); nan |= x != x; m0 = x > m0 ? x : m0; }
+        for (int v = V4; v < vb; ++v) { const float x = __uint_as_float(wr[v]); nan |= x != x; m0 = x > m0 ? x : m0; }
       } else {
         // 16-bit logits: unpack WORD by word (two symbols per 32-bit load, two instructions per symbol) into the emission
         // row as floats; the exp pass below reads them back.  (Unpacking symbol by symbol, twice, was half of all the
         // instructions BASELINE config 3 executed.)  Symbol v sits in halfword shift + v of the staged row.
-        const int nw = (shift + p.V + 1) >> 1;
+        const int k0 = ((shift + va) >> 1) & ~1, nw = (shift + vb + 1) >> 1;
         const bool bf = p.dtype == E2E_BF16;
-        for (int k = 0; k < nw; k += 2) {
+        for (int k = k0; k < nw; k += 2) {
           const uint32_t w0 = wr[k], w1 = k + 1 < nw ? wr[k + 1] : 0u;
           float a0, a1, a2, a3;
           if (bf) { a0 = __uint_as_float(w0 << 16); a1 = __uint_as_float(w0 & 0xffff0000u); a2 = __uint_as_float(w1 << 16); a3 = __uint_as_float(w1 & 0xffff0000u); }
@@ -205,26 +213,38 @@ __device__ __forceinline__ double convert_chunk(const SweepParams& p, const Chun
             a0 = f0.x; a1 = f0.y; a2 = f1.x; a3 = f1.y;
           }
           const int v0 = 2 * k - shift;
-          if (v0 >= 0 && v0 < p.V) { Ef[v0] = a0; nan |= a0 != a0; m0 = a0 > m0 ? a0 : m0; }
-          if (v0 + 1 < p.V) { Ef[v0 + 1] = a1; nan |= a1 != a1; m1 = a1 > m1 ? a1 : m1; }
-          if (v0 + 2 < p.V) { Ef[v0 + 2] = a2; nan |= a2 != a2; m2 = a2 > m2 ? a2 : m2; }
-          if (v0 + 3 < p.V) { Ef[v0 + 3] = a3; nan |= a3 != a3; m3 = a3 > m3 ? a3 : m3; }
+          if (v0 >= va && v0 < vb) { Ef[v0] = a0; nan |= a0 != a0; m0 = a0 > m0 ? a0 : m0; }
+          if (v0 + 1 >= va && v0 + 1 < vb) { Ef[v0 + 1] = a1; nan |= a1 != a1; m1 = a1 > m1 ? a1 : m1; }
+          if (v0 + 2 >= va && v0 + 2 < vb) { Ef[v0 + 2] = a2; nan |= a2 != a2; m2 = a2 > m2 ? a2 : m2; }
+          if (v0 + 3 >= va && v0 + 3 < vb) { Ef[v0 + 3] = a3; nan |= a3 != a3; m3 = a3 > m3 ? a3 : m3; }
         }
       }
       auto elem = [&](int v) -> float { return f32 ? __uint_as_float(wr[v]) : Ef[v]; };
-      const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      for (int o = p.cf; o < 32; o <<= 1) {      // the frame's other lanes (none when a lane owns the whole row)
+        m = fmaxf(m, __shfl_xor_sync(grp, m, o));
+        nan |= __shfl_xor_sync(grp, (int)nan, o) != 0;
+      }
       // exp(x - max) once per symbol: kept in the emission row, normalised below
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      for (int v = 0; v < V4; v += 4) {
+      for (int v = va; v < V4; v += 4) {
         const float e0 = expf(elem(v) - m), e1 = expf(elem(v + 1) - m), e2 = expf(elem(v + 2) - m), e3 = expf(elem(v + 3) - m);
         Ef[v] = e0; Ef[v + 1] = e1; Ef[v + 2] = e2; Ef[v + 3] = e3;
         s0 += e0; s1 += e1; s2 += e2; s3 += e3;
       }
-      for (int v = V4; v < p.V; ++v) { const float ev = expf(elem(v) - m); Ef[v] = ev; s0 += ev; }
-      const float s = (s0 + s1) + (s2 + s3);
+      for (int v = V4; v < vb; ++v) { const float ev = expf(elem(v) - m); Ef[v] = ev; s0 += ev; }
+      float s = (s0 + s1) + (s2 + s3);
+      if (lpf == 2) {         // partial sums of the frame's lanes, added in lane order: the same bits on every lane
+        const float q0 = __shfl_sync(grp, s, f), q1 = __shfl_sync(grp, s, f + p.cf);
+        s = q0 + q1;
+      } else if (lpf == 4) {
+        const float q0 = __shfl_sync(grp, s, f), q1 = __shfl_sync(grp, s, f + p.cf), q2 = __shfl_sync(grp, s, f + 2 * p.cf), q3 = __shfl_sync(grp, s, f + 3 * p.cf);
+        s = (q0 + q1) + (q2 + q3);
+      }
       float inv = 1.f / s;
       if (nan) inv = NAN;
-      for (int v = 0; v < p.V; ++v) Ef[v] *= inv;
+      for (int v = va; v < vb; ++v) Ef[v] *= inv;
+      if (sub != 0) return lse_part;       // the frame's first lane reports the row normaliser
       if (!p.from_logits) {
         const double mls = (double)m + (double)logf(s);
         cx.rs[f] = nan ? NAN : (float)exp(mls);
