@@ -620,6 +620,38 @@ int e2e_ctc_greedy_decode_device(const e2e_ctc_desc* desc, const void* logits, c
                        reinterpret_cast<char*>(workspace), reinterpret_cast<cudaStream_t>(cuda_stream));
 }
 
+// ---- LM-free prefix beam search -----------------------------------------------------------
+static int check_beam(const e2e_ctc_desc* desc, int32_t beam_width, int32_t space_idx, double wip) {
+  int rc = check_desc(desc, false);
+  if (rc != E2E_OK) return rc;
+  if (beam_width < 1) { set_error("beam_width %d < 1", beam_width); return E2E_ERR_INVALID_ARGUMENT; }
+  if (space_idx < -1 || space_idx >= desc->alphabet) { set_error("space_idx %d outside [-1,%d)", space_idx, desc->alphabet); return E2E_ERR_INVALID_ARGUMENT; }
+  if (!(wip == wip) || wip == INFINITY || wip == -INFINITY) { set_error("wip must be finite"); return E2E_ERR_INVALID_ARGUMENT; }
+  if (!beam_supported(*desc, beam_width)) {
+    set_error("beam search: beam_width %d with alphabet %d exceeds this build's limits (beam_width <= 256, beam and bitmap state <= 200 KB of shared memory)",
+              beam_width, desc->alphabet);
+    return E2E_ERR_UNSUPPORTED;
+  }
+  return E2E_OK;
+}
+
+size_t e2e_ctc_beam_workspace_bytes(const e2e_ctc_desc* desc, int32_t beam_width) {
+  if (check_beam(desc, beam_width, -1, 0.0) != E2E_OK) return 0;
+  return align256(beam_workspace_bytes(*desc, beam_width));
+}
+
+int e2e_ctc_beam_decode_device(const e2e_ctc_desc* desc, int32_t beam_width, int32_t space_idx, double wip,
+                               const void* logits, const void* logits_lengths, int64_t* decoded, int64_t* decoded_lengths,
+                               int64_t* ties, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  int rc = check_beam(desc, beam_width, space_idx, wip);
+  if (rc != E2E_OK) return rc;
+  if (!logits || !decoded || !decoded_lengths) { set_error("null pointer argument"); return E2E_ERR_INVALID_ARGUMENT; }
+  rc = check_ws(workspace, workspace_bytes, e2e_ctc_beam_workspace_bytes(desc, beam_width));
+  if (rc != E2E_OK) return rc;
+  return launch_beam(*desc, beam_width, space_idx, wip, logits, logits_lengths, decoded, decoded_lengths, ties,
+                     reinterpret_cast<char*>(workspace), reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
 // ---- pinned host memory for result buffers -------------------------------------------------------
 // The host-buffer entry points write their results straight into PINNED caller buffers (see e2e_ctc_engine_loss_host);
 // a binding that has no pinned allocator of its own takes its result buffers from here.
@@ -1024,6 +1056,42 @@ int e2e_ctc_engine_greedy_host(e2e_ctc_engine* e, const e2e_ctc_desc* desc, cons
   E2E_CUDA_TRY(cudaStreamSynchronize(s));
   e->h2d = n_log + (logits_lengths ? n_len : 0);
   e->d2h = n_dec + n_dl;
+  return E2E_OK;
+}
+
+int e2e_ctc_engine_beam_host(e2e_ctc_engine* e, const e2e_ctc_desc* desc, int32_t beam_width, int32_t space_idx, double wip,
+                             const void* logits, const void* logits_lengths, int64_t* decoded, int64_t* decoded_lengths,
+                             int64_t* ties) {
+  if (!e) { set_error("null engine"); return E2E_ERR_INVALID_ARGUMENT; }
+  int rc = check_beam(desc, beam_width, space_idx, wip);
+  if (rc != E2E_OK) return rc;
+  if (!logits || !decoded || !decoded_lengths) { set_error("null pointer argument"); return E2E_ERR_INVALID_ARGUMENT; }
+  const e2e_ctc_desc& d = *desc;
+  if (!dense_block(d, d.logits_stride_b, d.logits_stride_t)) {
+    set_error("host logits must be dense (batch-major or time-major contiguous)");
+    return E2E_ERR_INVALID_ARGUMENT;
+  }
+  E2E_CUDA_TRY(cudaSetDevice(e->device));
+  const size_t n_log = (size_t)d.batch * d.max_frames * d.alphabet * elem_size(d.dtype);
+  const size_t n_len = (size_t)d.batch * (d.lengths_itype == E2E_I64 ? 8 : 4);
+  const size_t n_dec = (size_t)d.batch * d.max_frames * 8, n_dl = (size_t)d.batch * 8;
+  const size_t n_ws = e2e_ctc_beam_workspace_bytes(desc, beam_width);
+  if ((rc = e->logits.ensure(n_log)) || (rc = e->in_len.ensure(n_len)) || (rc = e->decoded.ensure(n_dec)) ||
+      (rc = e->decoded_len.ensure(2 * n_dl)) || (rc = e->ws.ensure(n_ws)))
+    return rc;
+  cudaStream_t s = e->stream;
+  E2E_CUDA_TRY(cudaMemcpyAsync(e->logits.p, logits, n_log, cudaMemcpyHostToDevice, s));
+  if (logits_lengths) E2E_CUDA_TRY(cudaMemcpyAsync(e->in_len.p, logits_lengths, n_len, cudaMemcpyHostToDevice, s));
+  int64_t* d_len = reinterpret_cast<int64_t*>(e->decoded_len.p);
+  rc = launch_beam(d, beam_width, space_idx, wip, e->logits.p, logits_lengths ? e->in_len.p : nullptr,
+                   reinterpret_cast<int64_t*>(e->decoded.p), d_len, d_len + d.batch, reinterpret_cast<char*>(e->ws.p), s);
+  if (rc != E2E_OK) return rc;
+  E2E_CUDA_TRY(cudaMemcpyAsync(decoded, e->decoded.p, n_dec, cudaMemcpyDeviceToHost, s));
+  E2E_CUDA_TRY(cudaMemcpyAsync(decoded_lengths, d_len, n_dl, cudaMemcpyDeviceToHost, s));
+  if (ties) E2E_CUDA_TRY(cudaMemcpyAsync(ties, d_len + d.batch, n_dl, cudaMemcpyDeviceToHost, s));
+  E2E_CUDA_TRY(cudaStreamSynchronize(s));
+  e->h2d = n_log + (logits_lengths ? n_len : 0);
+  e->d2h = n_dec + n_dl + (ties ? n_dl : 0);
   return E2E_OK;
 }
 

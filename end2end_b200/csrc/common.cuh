@@ -104,7 +104,7 @@ constexpr int kFlagInfeasible = 1, kFlagInvalid = 2;
 void set_error(const char* fmt, ...);
 
 // Launch accounting + optional per-kernel device timing (CUDA events on the launching stream).
-enum { kKernelRowStats = 0, kKernelLattice, kKernelGrad, kKernelReduce, kKernelArgmax, kKernelCollapse, kKernelScale, kKernelViterbi, kKernelNoBlank, kNumKernels };
+enum { kKernelRowStats = 0, kKernelLattice, kKernelGrad, kKernelReduce, kKernelArgmax, kKernelCollapse, kKernelScale, kKernelViterbi, kKernelNoBlank, kKernelBeam, kNumKernels };
 void launch_begin(int kind, cudaStream_t s);
 void launch_end(int kind, cudaStream_t s);
 struct KernelTimer {   // brackets exactly one kernel launch
@@ -238,6 +238,10 @@ int launch_reduce(const void* losses, int dtype, int B, double scale, void* out,
                   cudaStream_t s);
 int launch_greedy(const e2e_ctc_desc& d, const void* logits, const void* in_len, int64_t* decoded,
                   int64_t* decoded_len, char* ws, cudaStream_t s);
+size_t beam_workspace_bytes(const e2e_ctc_desc& d, int beam_width);
+bool beam_supported(const e2e_ctc_desc& d, int beam_width);
+int launch_beam(const e2e_ctc_desc& d, int beam_width, int space_idx, double wip, const void* logits, const void* in_len,
+                int64_t* decoded, int64_t* decoded_len, int64_t* ties, char* ws, cudaStream_t s);
 size_t noblank_workspace_bytes(const e2e_ctc_desc& d);
 int launch_noblank(const e2e_ctc_desc& d, int space_idx, const void* lp, const void* targets, const void* in_len,
                    const void* tgt_len, void* losses, void* grads, char* ws, cudaStream_t s);

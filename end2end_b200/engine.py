@@ -576,3 +576,85 @@ class CTCGreedyEngine:
         _lib.check(self._L.e2e_ctc_engine_greedy_host(h.handle, ctypes.byref(d), _ptr(logits), _ptr(lengths_in),
                                                       _ptr(decoded), _ptr(lengths)))
         return decoded, lengths
+
+
+class CTCBeamEngine(CTCGreedyEngine):
+    """``cpp_ctc_decoder.CTCDecoder(blank_idx, beam_width_, labels, lm_path="", lmwt_, wip_, oov_penalty_,
+    case_sensitive)`` without a language model (src/decoders/ctc_decoder_py.cpp:5-39): ``decode(logits_,
+    logits_lengths_)`` is the prefix beam search of src/decoders/ctc_decoder.cpp:153-198,353-441 on the GPU and
+    ``decode_greedy`` the inherited greedy path.  Returns CPU int64 tensors like the reference:
+    ``(decoded_targets [B, max length] zero padded, decoded_targets_lengths [B])``; the sentences are assembled by
+    the Python wrapper.  ``last_ties`` holds, per utterance of the last call, how many prunes had equal scores on
+    both sides of the cut (where the reference's pick is libstdc++'s; see include/e2e_ctc.h)."""
+
+    def __init__(self, blank_idx=0, beam_width=100, labels=None, wip=0.0):
+        super().__init__(blank_idx)
+        self.beam_width = int(beam_width)
+        if self.beam_width < 1:
+            raise ValueError("beam_width must be >= 1")
+        labels = list(labels or [])
+        # ctc_decoder.cpp:56-60: space_id = index of " " in labels, -1 when there is none
+        self.space_idx = labels.index(" ") if " " in labels else -1
+        self.wip = float(wip)
+        self.last_ties = None
+
+    def _beam_desc(self, logits, lengths, from_logits):
+        d = self._desc(logits, lengths)
+        d.from_logits = 1 if from_logits else 0
+        if not -1 <= self.space_idx < logits.size(2):
+            raise ValueError("the space label %d is outside the alphabet [0,%d)" % (self.space_idx, logits.size(2)))
+        return d
+
+    def decode_device(self, logits, logits_lengths=None, from_logits=False):
+        """Device tensors in, device tensors out (no synchronisation): ``(decoded [B,T] int64 zero padded, lengths [B],
+        ties [B])``."""
+        _require_cuda()
+        logits = logits.detach()
+        dev = logits.device
+        if not _dense3(logits):
+            logits = logits.contiguous()
+        if logits_lengths is not None:
+            logits_lengths = _as_index(logits_lengths, dev, "logits_lengths").contiguous()
+        d = self._beam_desc(logits, logits_lengths, from_logits)
+        B, T = logits.size(0), logits.size(1)
+        with _on_device(dev):
+            need = self._L.e2e_ctc_beam_workspace_bytes(ctypes.byref(d), self.beam_width)
+            if need == 0:
+                raise _lib.E2EError(_lib.E2E_ERR_UNSUPPORTED, self._L.e2e_last_error_string().decode("utf-8", "replace"))
+            decoded = torch.empty(B, T, dtype=torch.int64, device=dev)
+            lengths = torch.empty(B, dtype=torch.int64, device=dev)
+            ties = torch.empty(B, dtype=torch.int64, device=dev)
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            _lib.check(self._L.e2e_ctc_beam_decode_device(
+                ctypes.byref(d), self.beam_width, self.space_idx, self.wip, _ptr(logits), _ptr(logits_lengths),
+                _ptr(decoded), _ptr(lengths), _ptr(ties), _ptr(ws), ws.numel(), _stream(dev)))
+        return decoded, lengths, ties
+
+    def decode(self, logits_, logits_lengths_=None, from_logits=False):
+        _require_cuda()
+        logits = logits_.detach()
+        if logits.is_cuda:
+            decoded, lengths, ties = self.decode_device(logits, logits_lengths_, from_logits)
+            decoded, lengths, ties = decoded.cpu(), lengths.cpu(), ties.cpu()
+        else:
+            if not (logits.is_contiguous() or logits.permute(1, 0, 2).is_contiguous()):
+                logits = logits.contiguous()
+            lengths_in = None
+            if logits_lengths_ is not None:
+                lengths_in = _as_index(logits_lengths_, torch.device("cpu"), "logits_lengths").contiguous()
+            d = self._beam_desc(logits, lengths_in, from_logits)
+            B, T = logits.size(0), logits.size(1)
+            decoded = torch.empty(B, T, dtype=torch.int64, pin_memory=True)
+            lengths = torch.empty(B, dtype=torch.int64, pin_memory=True)
+            ties = torch.empty(B, dtype=torch.int64, pin_memory=True)
+            dev = torch.cuda.current_device()
+            h = self._host.get(dev)
+            if h is None:
+                h = self._host[dev] = _HostEngine(dev)
+            _lib.check(self._L.e2e_ctc_engine_beam_host(h.handle, ctypes.byref(d), self.beam_width, self.space_idx,
+                                                        self.wip, _ptr(logits), _ptr(lengths_in), _ptr(decoded),
+                                                        _ptr(lengths), _ptr(ties)))
+        self.last_ties = ties
+        # ctc_decoder.cpp:186-196: the result matrix is as wide as the longest decoded sequence
+        width = int(lengths.max()) if lengths.numel() else 0
+        return decoded[:, :width].contiguous(), lengths

@@ -227,6 +227,33 @@ int e2e_ctc_greedy_decode_device(const e2e_ctc_desc* desc, const void* logits,
                                  int64_t* decoded_lengths, void* workspace, size_t workspace_bytes,
                                  void* cuda_stream);
 
+/* ------------------------------------------------------- LM-free prefix beam search, device ----- */
+
+/* Prefix beam search without a language model -- the reference's cpp_ctc_decoder.CTCDecoder(...).decode(logits_,
+ * logits_lengths_) (src/decoders/ctc_decoder_py.cpp:30-34; src/decoders/ctc_decoder.cpp:153-198 decode, :353-441
+ * decode_sentence, :241-309 get_next_prefix, :311-340 scores) with lm_path == "" (lmwt forced to 0, :76).
+ *   logits: log-probabilities [B,T,V] (desc strides) when desc->from_logits == 0 -- what the reference's C++ receives --
+ *       or raw logits when desc->from_logits == 1: the F.log_softmax of decoders/ctc_decoder.py:95-97 is then fused
+ *       (computed in the input's precision and rounded to the input dtype, as torch does);
+ *   beam_width: CTCDecoder's beam_width_ (>= 1; limits: e2e_ctc_beam_workspace_bytes returns 0 when unsupported);
+ *   space_idx: index of " " in the labels or -1 (ctc_decoder.cpp:56-60) -- only the word count behind `wip` uses it;
+ *   wip: word insertion penalty (score = log p(prefix) - num_words * wip, :311-315);
+ *   decoded: [B,T] int64 zero padded; decoded_lengths: [B] int64.  The reference returns [B, max length]: the caller
+ *       slices.  An utterance whose best prefix is EMPTY yields length 1 and the single symbol -1, as the reference does
+ *       (Prefix::get_sentence pushes the root's last_char, :225-239);
+ *   ties (optional, [B] int64): how many prunes of the utterance (and the final pick) had EQUAL scores on both sides of
+ *       the cut.  There the reference's choice is whatever libstdc++'s std::nth_element / std::sort do; this library
+ *       takes the lower position (beam order, then extensions by (member, symbol)).  0 = the result does not depend on
+ *       that.  In practice ties arise only between -inf scores while fewer than beam_width prefixes are feasible (tiny
+ *       alphabets with large beams) or from identical input rows.
+ * The prefix trie (node = parent, symbol, reference count, child list) lives in the workspace: the reference's
+ * weak_ptr lookup of a pruned-but-still-referenced child (:244-246) is reproduced exactly. */
+size_t e2e_ctc_beam_workspace_bytes(const e2e_ctc_desc* desc, int32_t beam_width);
+int e2e_ctc_beam_decode_device(const e2e_ctc_desc* desc, int32_t beam_width, int32_t space_idx, double wip,
+                               const void* logits, const void* logits_lengths, int64_t* decoded,
+                               int64_t* decoded_lengths, int64_t* ties, void* workspace, size_t workspace_bytes,
+                               void* cuda_stream);
+
 /* -------------------------------------------------------------- engine, host pointers ------ */
 
 typedef struct e2e_ctc_engine e2e_ctc_engine;
@@ -249,6 +276,11 @@ int e2e_ctc_engine_greedy_host(e2e_ctc_engine* engine, const e2e_ctc_desc* desc,
                                const void* logits_lengths, int64_t* decoded,
                                int64_t* decoded_lengths);
 
+/* Host-buffer form of CTCDecoder.decode() without a language model (see e2e_ctc_beam_decode_device). */
+int e2e_ctc_engine_beam_host(e2e_ctc_engine* engine, const e2e_ctc_desc* desc, int32_t beam_width, int32_t space_idx,
+                             double wip, const void* logits, const void* logits_lengths, int64_t* decoded,
+                             int64_t* decoded_lengths, int64_t* ties);
+
 /* Pinned (page-locked, device-addressable) host memory for result buffers: when `losses` / `grads` of
  * e2e_ctc_engine_loss_host live in such memory the kernels store into them directly and no copy-out stage runs. */
 int e2e_ctc_host_alloc(size_t bytes, void** out);
@@ -266,8 +298,8 @@ uint64_t e2e_ctc_launch_count(void);
 /* Optional per-kernel device timing for benchmarks.  While enabled, every kernel launch is
  * bracketed by CUDA events on its launching stream.  e2e_ctc_profile_read() waits for the pending
  * events, then fills ms[k] (summed device milliseconds) and launches[k] per kernel kind
- * k = 0 row_stats, 1 lattice, 2 gradient, 3 loss_reduce, 4 argmax, 5 collapse, 6 scale_rows
- * (n_kinds >= 9),
+ * k = 0 row_stats, 1 lattice, 2 gradient, 3 loss_reduce, 4 argmax, 5 collapse, 6 scale_rows, 7 viterbi,
+ * 8 ctc_without_blank, 9 beam_search (n_kinds >= 10),
  * and clears the record.  All launches since the previous read must have been made on ONE device. */
 int e2e_ctc_profile_enable(int32_t on);
 int e2e_ctc_profile_read(double* ms, uint64_t* launches, int32_t n_kinds);

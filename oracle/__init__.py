@@ -58,6 +58,9 @@ def lib():
         L.ctc_oracle_noblank.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.c_int, ctypes.c_int, ctypes.c_int, ip, ctypes.c_int,
                                          ip, ip, ctypes.c_int, dp, dp]
         L.ctc_oracle_noblank.restype = None
+        L.ctc_oracle_beam.argtypes = [dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ip, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_double, ctypes.c_double, ip, ip, ip]
+        L.ctc_oracle_beam.restype = None
         _lib = L
     return _lib
 
@@ -262,3 +265,44 @@ def ctc_without_blank(log_probs, targets, logits_lengths, targets_lengths, space
     lib().ctc_oracle_noblank(lp.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), B, T, V, _iptr(tg), Lmax, _iptr(il), _iptr(tl),
                              int(space_idx), _dptr(losses), _dptr(grads))
     return torch.from_numpy(losses), torch.from_numpy(grads)
+
+
+def _space_id(labels):
+    # src/decoders/ctc_decoder.cpp:56-60: index of " " in labels, -1 without labels / without a space
+    labels = list(labels or [])
+    return labels.index(" ") if " " in labels else -1
+
+
+def beam_decode(logits, logits_lengths=None, blank_idx=0, beam_width=100, time_major=False, labels=None,
+                after_logsoftmax=False, wip=0.0, oov_penalty=-1000.0, prefer="reference", return_ties=False):
+    """decoders/ctc_decoder.py:76-115 (decode, LM-free) + ctc_decoder.cpp:153-198,353-441.  Returns (targets
+    [B, max length] i64 zero padded, lengths [B] i64, sentences).  ``prefer="reference"`` runs the compiled
+    reference when oracle/_ref travelled with the repo, else the C restatement."""
+    with torch.no_grad():
+        if not after_logsoftmax:
+            logits = F.log_softmax(logits, -1)
+        if time_major:
+            logits = logits.transpose(1, 0)
+    logits = logits.detach().cpu()
+    B, T, V = logits.shape
+    if logits_lengths is None:
+        logits_lengths = torch.zeros(B, dtype=torch.int).fill_(T)
+    logits_lengths = logits_lengths.cpu()
+    labels = list(labels or [])
+    mod = _load_ref("cpp_ctc_decoder", "decoder") if prefer == "reference" else None
+    if mod is not None:
+        dec = mod.CTCDecoder(int(blank_idx), int(beam_width), labels, "", 1.0, float(wip), float(oov_penalty), False)
+        return dec.decode(logits_=logits.contiguous(), logits_lengths_=logits_lengths)
+    x = np.ascontiguousarray(logits.to(torch.float64).numpy())
+    il = np.ascontiguousarray(logits_lengths.to(torch.int64).numpy())
+    Tw = max(T, 1)
+    out = np.zeros((B, Tw), dtype=np.int64)
+    out_len = np.zeros(B, dtype=np.int64)
+    ties = np.zeros(B, dtype=np.int64)
+    lib().ctc_oracle_beam(_dptr(x), B, T, V, _iptr(il), int(blank_idx), int(beam_width), _space_id(labels),
+                          float(wip), float(oov_penalty), _iptr(out), _iptr(out_len), _iptr(ties))
+    out = out[:, :max(int(out_len.max()), 0)] if B else out
+    sents = ["".join(labels[i] for i in out[b, :out_len[b]] if i >= 0) if labels else "" for b in range(B)]
+    if return_ties:
+        return torch.from_numpy(np.ascontiguousarray(out)), torch.from_numpy(out_len), sents, torch.from_numpy(ties)
+    return torch.from_numpy(np.ascontiguousarray(out)), torch.from_numpy(out_len), sents

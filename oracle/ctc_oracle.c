@@ -327,3 +327,172 @@ void ctc_oracle_noblank(const float* lp32, int B, int T, int V, const int64_t* t
     free(x);
   }
 }
+
+/*
+ * LM-free prefix beam search, one utterance: src/decoders/ctc_decoder.cpp:353-441 (decode_sentence) with
+ * get_next_prefix (:241-309, the lm_model == nullptr branch), Prefix::next_step / get_prev_full_prob (:331-340),
+ * get_prev_full_prob_with_lmwt (:311-315) and Prefix::get_sentence (:225-239).
+ *
+ * The reference keeps prefixes as shared_ptr objects; a child is found through a weak_ptr in its parent's
+ * `next_data`.  What that ownership model DOES is restated with explicit reference counts (BNode.refs: one for
+ * membership of the beam + one per living child, exactly the shared_ptr holders `prefixes` and `Prefix::parent`):
+ *   - a child that is still in the beam is found and accumulates (is_new == false, :244-246),
+ *   - a child that was pruned but is kept alive by a descendant in the beam is ALSO found, is not in the list,
+ *     and therefore swallows the extension: that prefix cannot re-enter the beam while the descendant lives
+ *     (a property of the reference, reproduced on purpose),
+ *   - a child whose last owner went away has expired: a fresh prefix is made (:248-308).
+ * The V-1 fresh prefixes every beam member makes per frame (:377-378) are records in a flat array here; only
+ * those that survive the prune become nodes (the others are created and destroyed within the frame in the
+ * reference, unobserved).  Scores: get_prev_full_prob() + lm_score*lmwt - num_words*wip + num_oov_words*oov_penalty
+ * with lm_score = 0, lmwt = 0 (ctc_decoder.cpp:76), num_oov_words = 0.
+ * Prune (:399-410) keeps the beam_width best; std::nth_element / std::sort leave the choice among EQUAL scores to
+ * the library -- here ties go to the lower position (beam members in beam order, then fresh prefixes by
+ * (member, symbol)), and the surviving list keeps that order.
+ * Result (:430-435): the symbols of the best prefix; the EMPTY prefix yields the single symbol -1 with length 1
+ * (get_sentence pushes last_char = -1 of the root), as the compiled reference returns.
+ */
+typedef struct BNode {
+  struct BNode *parent, *first_child, *next_sib;
+  int chr, refs, slot;
+} BNode;
+
+static void bnode_unref(BNode* n) {
+  while (n && --n->refs == 0) {
+    BNode* p = n->parent;
+    if (p) {  /* weak_ptr in the parent's next_data expires */
+      BNode** q = &p->first_child;
+      while (*q != n) q = &(*q)->next_sib;
+      *q = n->next_sib;
+    }
+    free(n);
+    n = p;
+  }
+}
+
+typedef struct { double score; int idx; } BKey;
+static int bkey_cmp(const void* a, const void* b) {
+  const BKey *x = (const BKey*)a, *y = (const BKey*)b;
+  if (x->score > y->score) return -1;
+  if (x->score < y->score) return 1;
+  return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0);
+}
+
+static double beam_score(double full, int num_words, double wip, double oov_penalty) {
+  return full + 0.0 * 0.0 - num_words * wip + 0 * oov_penalty;
+}
+
+static int beam_utterance(const double* lp, int V, int T, int blank, int beam_width, int space_id, double wip,
+                          double oov_penalty, int64_t* out, int64_t* ties) {
+  const size_t cap = (size_t)beam_width + 1;
+  int64_t n_ties = 0;   /* prunes (and the final pick) where EQUAL scores straddle the cut: the reference's choice is libstdc++'s */
+  BNode** node = (BNode**)malloc(sizeof(BNode*) * cap);
+  BNode** node2 = (BNode**)malloc(sizeof(BNode*) * cap);
+  double *pb = (double*)malloc(sizeof(double) * cap), *pnb = (double*)malloc(sizeof(double) * cap);
+  double *pb2 = (double*)malloc(sizeof(double) * cap), *pnb2 = (double*)malloc(sizeof(double) * cap);
+  double *npb = (double*)malloc(sizeof(double) * cap), *npnb = (double*)malloc(sizeof(double) * cap), *full = (double*)malloc(sizeof(double) * cap);
+  int *nw = (int*)malloc(sizeof(int) * cap), *nw2 = (int*)malloc(sizeof(int) * cap);
+  /* fresh prefixes of this frame, indexed member * V + symbol */
+  const size_t fcap = cap * (size_t)V;
+  double* f_pnb = (double*)malloc(sizeof(double) * fcap);
+  int* f_nw = (int*)malloc(sizeof(int) * fcap);
+  char* f_made = (char*)malloc(fcap);
+  char* alive = (char*)malloc(cap + fcap);
+  BKey* keys = (BKey*)malloc(sizeof(BKey) * (fcap + cap));
+
+  BNode* root = (BNode*)calloc(1, sizeof(BNode));   /* get_initial_prefix (:201-209) */
+  root->chr = -1; root->refs = 1; root->slot = 0;
+  int W = 1;
+  node[0] = root; pb[0] = 0.0; pnb[0] = NEG_INF; nw[0] = 0;
+
+  for (int t = 0; t < T; t++) {
+    const double* row = lp + (size_t)t * V;
+    for (int s = 0; s < W; s++) { full[s] = lse2(pnb[s], pb[s]); npb[s] = NEG_INF; npnb[s] = NEG_INF; }
+    memset(f_made, 0, (size_t)W * V);
+    for (int c = 0; c < V; c++) {          /* for every character (:368) */
+      const double cur = row[c];
+      for (int s = 0; s < W; s++) {        /* for every prefix (:371) */
+        if (c == blank) { npb[s] = lse2(npb[s], cur + full[s]); continue; }
+        BNode* ch = node[s]->first_child;  /* get_next_prefix (:244-246): a living child is found */
+        while (ch && ch->chr != c) ch = ch->next_sib;
+        double sink = NEG_INF, *target;
+        if (ch) target = ch->slot >= 0 ? &npnb[ch->slot] : &sink;   /* in the beam, or kept alive by a descendant */
+        else {
+          const size_t f = (size_t)s * V + c;
+          f_made[f] = 1; f_pnb[f] = NEG_INF;
+          f_nw[f] = nw[s] + ((c != space_id && (nw[s] == 0 || node[s]->chr == space_id)) ? 1 : 0);   /* :252-257 */
+          target = &f_pnb[f];
+        }
+        if (c == node[s]->chr) {   /* repeated character (:381-385) */
+          *target = lse2(*target, cur + pb[s]);
+          npnb[s] = lse2(npnb[s], cur + pnb[s]);
+        } else {
+          *target = lse2(*target, cur + full[s]);
+        }
+      }
+    }
+    /* next_step for everybody (:397), then the prune (:399-410) */
+    int total = 0;
+    for (int s = 0; s < W; s++) { keys[total].score = beam_score(lse2(npnb[s], npb[s]), nw[s], wip, oov_penalty); keys[total++].idx = s; }
+    for (size_t f = 0; f < (size_t)W * V; f++)
+      if (f_made[f]) { keys[total].score = beam_score(lse2(f_pnb[f], NEG_INF), f_nw[f], wip, oov_penalty); keys[total++].idx = W + (int)f; }
+    int keep = total;
+    if (total > beam_width) {
+      qsort(keys, (size_t)total, sizeof(BKey), bkey_cmp);
+      keep = beam_width;
+      if (keys[keep - 1].score == keys[keep].score) n_ties++;
+    }
+    memset(alive, 0, (size_t)W + (size_t)W * V);
+    for (int i = 0; i < keep; i++) alive[keys[i].idx] = 1;
+    int W2 = 0;   /* the surviving list, in position order */
+    for (int s = 0; s < W; s++)
+      if (alive[s]) { node2[W2] = node[s]; pb2[W2] = npb[s]; pnb2[W2] = npnb[s]; nw2[W2] = nw[s]; W2++; }
+    for (int s = 0; s < W; s++)
+      for (int c = 0; c < V; c++) {
+        const size_t f = (size_t)s * V + c;
+        if (!f_made[f] || !alive[W + f]) continue;
+        BNode* n = (BNode*)calloc(1, sizeof(BNode));
+        n->chr = c; n->refs = 1; n->parent = node[s]; node[s]->refs++;
+        n->next_sib = node[s]->first_child; node[s]->first_child = n;
+        node2[W2] = n; pb2[W2] = NEG_INF; pnb2[W2] = f_pnb[f]; nw2[W2] = f_nw[f]; W2++;
+      }
+    for (int s = 0; s < W; s++) if (!alive[s]) { node[s]->slot = -1; bnode_unref(node[s]); }
+    W = W2;
+    for (int s = 0; s < W; s++) { node[s] = node2[s]; node[s]->slot = s; pb[s] = pb2[s]; pnb[s] = pnb2[s]; nw[s] = nw2[s]; }
+  }
+
+  int best = 0;   /* std::sort (:413-419) + prefixes[0] */
+  double best_score = beam_score(lse2(pnb[0], pb[0]), nw[0], wip, oov_penalty);
+  for (int s = 1; s < W; s++) {
+    const double sc = beam_score(lse2(pnb[s], pb[s]), nw[s], wip, oov_penalty);
+    if (sc > best_score) { best_score = sc; best = s; }
+  }
+  for (int s = 0; s < W; s++)
+    if (s != best && beam_score(lse2(pnb[s], pb[s]), nw[s], wip, oov_penalty) == best_score) { n_ties++; break; }
+  if (ties) *ties = n_ties;
+  /* get_sentence (:225-239): last_char of the prefix, then of every ancestor except the root */
+  int n = 0;
+  for (BNode* p = node[best]; p; p = p->parent) if (p == node[best] || p->parent) n++;
+  int k = n;
+  for (BNode* p = node[best]; p; p = p->parent) if (p == node[best] || p->parent) out[--k] = p->chr;
+  for (int s = 0; s < W; s++) bnode_unref(node[s]);
+  free(node); free(node2); free(pb); free(pnb); free(pb2); free(pnb2); free(npb); free(npnb); free(full); free(nw); free(nw2);
+  free(f_pnb); free(f_nw); free(f_made); free(alive); free(keys);
+  return n;
+}
+
+/* CTCDecoder::decode (:153-198): out [B][Tw] zero-filled, Tw = max(T, 1); out_len [B].  lp are log-probabilities
+ * (the Python wrapper has applied log_softmax: decoders/ctc_decoder.py:95-97).  ties [B] (optional): how many prunes of
+ * the utterance had equal scores on both sides of the cut (0: the result does not depend on the sort library). */
+void ctc_oracle_beam(const double* lp, int B, int T, int V, const int64_t* in_len, int blank, int beam_width, int space_id,
+                     double wip, double oov_penalty, int64_t* out, int64_t* out_len, int64_t* ties) {
+  const int Tw = T > 1 ? T : 1;
+  memset(out, 0, sizeof(int64_t) * (size_t)B * Tw);
+#pragma omp parallel for schedule(dynamic)
+  for (int b = 0; b < B; b++) {
+    int Ti = (int)in_len[b];
+    if (Ti > T) Ti = T;
+    if (Ti < 0) Ti = 0;
+    out_len[b] = beam_utterance(lp + (size_t)b * T * V, V, Ti, blank, beam_width, space_id, wip, oov_penalty, out + (size_t)b * Tw,
+                                ties ? ties + b : NULL);
+  }
+}

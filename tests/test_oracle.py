@@ -202,3 +202,59 @@ def test_noblank_oracle_matches_reference_goldens(name):
     ok = ~torch.isnan(rg)
     # the reference's grads array has the dtype of its float32 input (np.zeros_like(logits)): one float32 rounding
     torch.testing.assert_close(grads[ok], rg[ok], rtol=0, atol=2e-7)
+
+
+# --------------------------------------------------------------------------------------------
+# LM-free prefix beam search: the C restatement against the compiled reference
+# --------------------------------------------------------------------------------------------
+BEAM_GOLDENS = sorted(os.path.basename(p)[:-4] for p in __import__("glob").glob(os.path.join(GOLD, "beam_*.npz")))
+
+
+@pytest.mark.parametrize("name", BEAM_GOLDENS)
+def test_beam_oracle_matches_reference_goldens(name):
+    """tests/golden/beam_*.npz hold what the reference's compiled decoder returned (make_beam_golden.py).  Every
+    utterance whose prunes never had equal scores on both sides of the cut must be reproduced symbol for symbol."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    labels = str(g["labels"]).split("\x1f") if str(g["labels"]) else []
+    tgt, tl, sents, ties = oracle.beam_decode(torch.from_numpy(g["log_probs"]), torch.from_numpy(g["logits_lengths"]),
+                                              blank_idx=int(g["blank"]), beam_width=int(g["beam"]), labels=labels,
+                                              after_logsoftmax=True, wip=float(g["wip"]), prefer="port", return_ties=True)
+    assert torch.equal(ties, torch.from_numpy(g["ties"]))
+    want_t, want_l = torch.from_numpy(g["targets"]), torch.from_numpy(g["targets_lengths"])
+    n_free = 0
+    for i in range(tl.numel()):
+        if ties[i] == 0:
+            n_free += 1
+            assert int(tl[i]) == int(want_l[i]) and tgt[i, :int(tl[i])].tolist() == want_t[i, :int(tl[i])].tolist(), i
+    assert n_free > 0 or "ties" in name
+    if n_free == tl.numel() and labels and int(want_t.min()) >= 0:
+        assert sents == str(g["sentences"]).split("\x1f")
+
+
+def test_beam_oracle_known_answers():
+    """The reference's own beam-search known answers (tests/test_ctc_decoder.py:86-166)."""
+    for name, want in (("beam_kat_sm", "a"), ("beam_kat_1", "acdc"), ("beam_kat_2", "b'a")):
+        g = np.load(os.path.join(GOLD, name + ".npz"))
+        labels = str(g["labels"]).split("\x1f")
+        out = oracle.beam_decode(torch.from_numpy(g["log_probs"]), torch.from_numpy(g["logits_lengths"]), blank_idx=int(g["blank"]),
+                                 beam_width=20, labels=labels, after_logsoftmax=True, wip=0.0, prefer="port")
+        assert out[2] == [want]
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
+def test_beam_oracle_differential_vs_compiled_reference():
+    """Random shapes: wherever the restatement reports no tie it equals the compiled reference."""
+    g = torch.Generator().manual_seed(123)
+    free = 0
+    for V in (3, 6, 29):
+        for beam in (2, 9, 100):
+            for T in (3, 25, 60):
+                lp = torch.log_softmax(torch.randn(2, T, V, generator=g) * 2.0, 2)
+                ll = torch.tensor([T, max(1, T - 2)])
+                a = oracle.beam_decode(lp, ll, beam_width=beam, after_logsoftmax=True, prefer="reference")
+                b = oracle.beam_decode(lp, ll, beam_width=beam, after_logsoftmax=True, prefer="port", return_ties=True)
+                for i in range(2):
+                    if b[3][i] == 0:
+                        free += 1
+                        assert int(a[1][i]) == int(b[1][i]) and a[0][i, :int(a[1][i])].tolist() == b[0][i, :int(b[1][i])].tolist()
+    assert free >= 40

@@ -38,6 +38,8 @@ def test_reference_test_ctc_unmodified():
 
 
 def test_reference_test_ctc_decoder_unmodified():
-    """The greedy known answer (tests/test_ctc_decoder.py:44-59)."""
-    out = _run("test_ctc_decoder", ["TestCTCDecoder.test_greedy_simple"])
-    assert "Ran 1 test" in out and "OK" in out, out[-2000:]
+    """The greedy known answer (tests/test_ctc_decoder.py:44-59) and the three LM-free prefix-beam known answers
+    (:86-166: greedy AND beam result of each case)."""
+    out = _run("test_ctc_decoder", ["TestCTCDecoder.test_greedy_simple", "TestCTCDecoder.test_with_probs_sm",
+                                    "TestCTCDecoder.test_with_probs_1", "TestCTCDecoder.test_with_probs_2"])
+    assert "Ran 4 tests" in out and "OK" in out, out[-2000:]
