@@ -659,6 +659,42 @@ def run_ours(args, wl):
                                    "cpu_baseline": {"value": a_cpu, "unit": "utterances/s", "kind": "port", "cores": os.cpu_count(),
                                                     "sample": "3 passes of the same batch, C restatement of the reference's numba code, "
                                                               "OpenMP over utterances (the reference: one Python thread per utterance)"}}
+            # ---- LM-free prefix beam search of the c2 logits, the reference's default beam of 100 ----
+            from end2end_b200.engine import CTCBeamEngine
+            beng = CTCBeamEngine(0, 100)
+            dx = ax.to(dev)
+            bdec, blen, bties = beng.decode_device(dx, dll, from_logits=True)
+            nb_chk = 4                                   # parity against the oracle on a few utterances (the CPU search is slow)
+            want = oracle.beam_decode(ax[:nb_chk], all_[:nb_chk], beam_width=100, after_logsoftmax=False, return_ties=True,
+                                      prefer="reference" if oracle.have_ref() else "port")
+            for i in range(nb_chk):
+                n_i = int(want[1][i])
+                assert int(blen[i]) == n_i and bdec[i, :n_i].cpu().tolist() == want[0][i, :n_i].tolist(), "beam search differs from the oracle"
+            _lib.profile_enable(True); _lib.profile_read()
+            for i in range(5):
+                flush_buf.add_(1)
+                beng.decode_device(dx, dll, from_logits=True)
+            torch.cuda.synchronize()
+            bprof = _lib.profile_read(); _lib.profile_enable(False)
+            b_ms = bprof["beam_search"][0] / max(1, bprof["beam_search"][1])
+            hx = ax.pin_memory()
+            beng.decode(hx, all_, from_logits=True)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                beng.decode(hx, all_, from_logits=True)
+            b_e2e = Ba * 3 / (time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            nb_cpu = min(Ba, 2 * (os.cpu_count() or 1))
+            oracle.beam_decode(ax[:nb_cpu], all_[:nb_cpu], beam_width=100, after_logsoftmax=False)
+            b_cpu = nb_cpu / (time.perf_counter() - t0)
+            extras["beam_search"] = {"workload": "LM-free prefix beam search (beam_width 100) of the c2 logits, B=%d T=%d V=%d fp32, log-softmax fused" % (Ba, Ta, Va),
+                                     "value": Ba / (b_ms * 1e-3), "unit": "utterances/s", "kernel_ms": b_ms, "e2e_value": b_e2e,
+                                     "bit_exact_vs_oracle": True, "checked_utterances": nb_chk, "ties": int(bties.sum()),
+                                     "l2": "L2 flushed between launches (256 MB write), kernel timed by the library's event hooks",
+                                     "cpu_baseline": {"value": b_cpu, "unit": "utterances/s", "cores": os.cpu_count(),
+                                                      "kind": "reference" if oracle.have_ref() else "port",
+                                                      "sample": "%d utterances of the same batch, one host thread per utterance (the reference's pool)" % nb_cpu}}
+            del dx, hx
         if not args.no_cpu_baseline:
             best, runs = measure_reference(wl, 0, 1, args.ref_batch, cpu_seconds=args.cpu_seconds / 2, greedy=False)
             if best:

@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("E2E_CTC_LIB") or os.path.join(_HERE, "lib", "libe2e_ctc.so")
 
 E2E_OK = 0
+E2E_ERR_UNSUPPORTED = 2
 E2E_ERR_LENGTHS = 5
 E2E_F32, E2E_BF16, E2E_F16, E2E_F64 = 0, 1, 2, 3
 E2E_I32, E2E_I64 = 0, 1

@@ -33,8 +33,8 @@
 namespace e2e {
 namespace {
 
-struct __align__(32) BeamNode {   // 32 bytes: one sector
-  int parent, chr, refs, slot, first_child, next_sib, depth, pad;
+struct __align__(16) BeamNode {   // 16 bytes
+  int parent, chr, refs, depth;
 };
 
 struct BeamParams {
@@ -49,8 +49,16 @@ struct BeamParams {
   double wip;
 };
 
-constexpr int kBeamThreads = 256;
-constexpr int kBeamWarps = kBeamThreads / 32;
+#ifndef E2E_BEAM_DIGIT
+#define E2E_BEAM_DIGIT 8
+#endif
+constexpr int kBeamMaxWidth = 256;     // beam members are handled one per thread by the first 256 threads
+constexpr int kBeamDigit = E2E_BEAM_DIGIT;          // radix-select digit, bits
+constexpr int kBeamBins = 1 << kBeamDigit;
+constexpr int kBeamTopShift = (63 / kBeamDigit) * kBeamDigit;
+static_assert(kBeamBins % 32 == 0 && kBeamBins <= 2048, "digit width");
+constexpr int kBeamPre = 4;        // symbols per thread of the next frame's row kept in flight (V <= 4 x threads)
+constexpr int kBeamKeyCache = 19200;   // extensions (beam x alphabet) whose keys are kept in shared memory (150 KB)
 
 __device__ __forceinline__ double beam_lse(double a, double b) {   // math_utils.h:8-16
   if (a == -INFINITY) return b;
@@ -64,17 +72,18 @@ __device__ __forceinline__ double beam_score(double full, int num_words, double 
   return __dsub_rn(__dadd_rn(full, 0.0), __dmul_rn((double)num_words, wip));
 }
 
-// order-preserving image of a double; +0 and -0 coincide, NaN sorts below everything
+// order-preserving image of a double, never 0 (0 marks "no candidate"); +0 and -0 coincide, NaN sorts below everything
 __device__ __forceinline__ unsigned long long beam_key(double x) {
-  if (x != x) return 0ull;
+  if (x != x) return 1ull;
   x = __dadd_rn(x, 0.0);
   const unsigned long long u = (unsigned long long)__double_as_longlong(x);
   return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
 }
 
-struct BeamBuf {          // one copy of the beam
+struct BeamBuf {          // one copy of the beam (+ the pruned prefixes that still block an extension of a member)
   double *pb, *pnb;
-  int *node, *last, *nw, *dep;
+  int *node, *par, *last, *nw, *dep, *pslot;   // trie node, parent node, last symbol, words, length, parent's slot or -1
+  int *zn, *zp, *zc;                           // blocked extensions: node, parent's slot, symbol
 };
 struct BeamSmem {
   double* lp;            // [Vp]
@@ -83,110 +92,109 @@ struct BeamSmem {
   int *nwx;              // word count of an extension with a symbol other than space
   int *cgt, *ceq;        // per position group: survivors above the cut / in the cut class (members: [0,W), rows: [W,2W))
   unsigned* bitmap;      // [W][VW] extensions that are not fresh prefixes
-  unsigned* hist;        // [256]
+  unsigned* hist;        // [kBeamBins]
+  double *penx, *pens;   // word penalty of an extension with a symbol other than space / with the space
+  unsigned long long* kc;   // [W][V] keys of the extensions (0: none) when they fit
 };
 
-__device__ __forceinline__ double ext_value(const BeamSmem& S, const BeamBuf& C, int s, int c, int last_s) {
-  // :381-390: a repeated character extends from the blank-ending mass only
-  return __dadd_rn(S.lp[c], c == last_s ? C.pb[s] : S.full[s]);
-}
+// :381-390: a repeated character extends from the blank-ending mass only
+#define BEAM_EXT_VALUE(c, last_s, pb_s, full_s) __dadd_rn(S.lp[c], (c) == (last_s) ? (pb_s) : (full_s))
 
-template <typename T>
-__global__ void __launch_bounds__(kBeamThreads) ctc_beam_kernel(const BeamParams p) {
+// NT threads per CTA: 512 when every utterance has an SM to itself (the frame chain is latency-bound: more warps hide more
+// of it), 256 for larger batches (several CTAs per SM)
+template <typename T, bool CACHE, int NT>
+__global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
+  constexpr int kBeamThreads = NT, kBeamWarps = NT / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ float s_red[kBeamWarps];
-  __shared__ unsigned long long s_thr;
-  __shared__ int s_sh, s_need, s_W, s_nodes, s_ties, s_total, s_done, s_keepm, s_keepall;
+  __shared__ unsigned long long s_thr, s_kmax, s_kmin;
+  __shared__ int s_need, s_W, s_nodes, s_ties, s_excl, s_done, s_keepm, s_keepall, s_nz, s_nz2, s_ovf;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int V = p.V, WB = p.beam, VW = (V + 31) >> 5, Vp = (V + 1) & ~1;
+  using raw_t = typename Elem<T>::acc_t;   // float for 32/16-bit inputs, double for f64
 
   BeamSmem S;
   BeamBuf C, N;
+  raw_t* raw;
   {
     unsigned char* q = smem_raw;
     auto take = [&](size_t bytes) { unsigned char* r = q; q += (bytes + 15) & ~(size_t)15; return r; };
     S.lp = reinterpret_cast<double*>(take(sizeof(double) * Vp));
+    raw = reinterpret_cast<raw_t*>(take(sizeof(double) * Vp));
     C.pb = reinterpret_cast<double*>(take(8 * WB)); C.pnb = reinterpret_cast<double*>(take(8 * WB));
     N.pb = reinterpret_cast<double*>(take(8 * WB)); N.pnb = reinterpret_cast<double*>(take(8 * WB));
     S.full = reinterpret_cast<double*>(take(8 * WB));
     S.npb = reinterpret_cast<double*>(take(8 * WB));
     S.npnb = reinterpret_cast<double*>(take(8 * WB));
     S.mkey = reinterpret_cast<unsigned long long*>(take(8 * WB));
-    C.node = reinterpret_cast<int*>(take(4 * WB)); C.last = reinterpret_cast<int*>(take(4 * WB));
-    C.nw = reinterpret_cast<int*>(take(4 * WB)); C.dep = reinterpret_cast<int*>(take(4 * WB));
-    N.node = reinterpret_cast<int*>(take(4 * WB)); N.last = reinterpret_cast<int*>(take(4 * WB));
-    N.nw = reinterpret_cast<int*>(take(4 * WB)); N.dep = reinterpret_cast<int*>(take(4 * WB));
+    int** cf[9] = {&C.node, &C.par, &C.last, &C.nw, &C.dep, &C.pslot, &C.zn, &C.zp, &C.zc};
+    int** nf[9] = {&N.node, &N.par, &N.last, &N.nw, &N.dep, &N.pslot, &N.zn, &N.zp, &N.zc};
+#pragma unroll
+    for (int k = 0; k < 9; k++) { *cf[k] = reinterpret_cast<int*>(take(4 * WB)); *nf[k] = reinterpret_cast<int*>(take(4 * WB)); }
     S.nwx = reinterpret_cast<int*>(take(4 * WB));
     S.cgt = reinterpret_cast<int*>(take(4 * 2 * WB));
     S.ceq = reinterpret_cast<int*>(take(4 * 2 * WB));
     S.bitmap = reinterpret_cast<unsigned*>(take((size_t)4 * WB * VW));
-    S.hist = reinterpret_cast<unsigned*>(take(4 * 256));
+    S.hist = reinterpret_cast<unsigned*>(take(4 * kBeamBins));
+    S.penx = reinterpret_cast<double*>(take(8 * WB)); S.pens = reinterpret_cast<double*>(take(8 * WB));
+    S.kc = reinterpret_cast<unsigned long long*>(take(CACHE ? (size_t)8 * WB * V : 0));
   }
 
   long long Ti_ll = p.in_len ? load_index(p.in_len, p.len_is64, b) : (long long)p.T;
   const int Ti = (int)max(0LL, min(Ti_ll, (long long)p.T));
   BeamNode* nodes = p.nodes + (long long)b * p.node_cap;
   const T* x = reinterpret_cast<const T*>(p.logits) + (long long)b * p.sb;
+  const bool use_pre = V <= kBeamThreads * kBeamPre;
 
   if (tid == 0) {   // get_initial_prefix (:201-209): the empty prefix with log p(blank) = 0
-    BeamNode r; r.parent = -1; r.chr = -1; r.refs = 1; r.slot = 0; r.first_child = -1; r.next_sib = -1; r.depth = 0; r.pad = 0;
+    BeamNode r; r.parent = -1; r.chr = -1; r.refs = 1; r.depth = 0;
     nodes[0] = r;
-    C.node[0] = 0; C.last[0] = -1; C.nw[0] = 0; C.dep[0] = 0; C.pb[0] = 0.0; C.pnb[0] = -INFINITY;
-    s_W = 1; s_nodes = 1; s_ties = 0;
+    C.node[0] = 0; C.par[0] = -1; C.last[0] = -1; C.nw[0] = 0; C.dep[0] = 0; C.pslot[0] = -1; C.pb[0] = 0.0; C.pnb[0] = -INFINITY;
+    s_W = 1; s_nodes = 1; s_ties = 0; s_nz = 0; s_ovf = 0;
+  }
+  raw_t pre[kBeamPre];
+#pragma unroll
+  for (int k = 0; k < kBeamPre; k++) {
+    const int c = tid + k * kBeamThreads;
+    pre[k] = (use_pre && Ti > 0 && c < V) ? (raw_t)Elem<T>::load(x + c) : (raw_t)0;
   }
   __syncthreads();
 
   for (int t = 0; t < Ti; t++) {
-    const int W = s_W;
-    // ---- the frame's log-probabilities (decoders/ctc_decoder.py:95-97 when the input is raw logits) ----------
+    const int W = s_W, nz = s_nz;
+    // ---- the frame's row: staged from the registers it was prefetched into; the next frame's row is requested now ------
     const T* row = x + (long long)t * p.st;
-    if (p.from_logits) {
-      if (sizeof(T) == 8) {   // fp64 input: the log-softmax in fp64
-        double m = -INFINITY;
-        for (int c = tid; c < V; c += kBeamThreads) m = fmax(m, (double)Elem<T>::load(row + c));
-        m = warp_max(m);
-        double* redd = reinterpret_cast<double*>(S.hist);   // 256 words: room for 8 doubles + broadcast
-        if (lane == 0) redd[warp] = m;
-        __syncthreads();
-        m = redd[0];
-        for (int w = 1; w < kBeamWarps; w++) m = fmax(m, redd[w]);
-        __syncthreads();
-        double sum = 0.0;
-        for (int c = tid; c < V; c += kBeamThreads) sum += exp((double)Elem<T>::load(row + c) - m);
-        sum = warp_sum(sum);
-        if (lane == 0) redd[warp] = sum;
-        __syncthreads();
-        sum = 0.0;
-        for (int w = 0; w < kBeamWarps; w++) sum += redd[w];
-        const double ls = log(sum);
-        for (int c = tid; c < V; c += kBeamThreads) S.lp[c] = ((double)Elem<T>::load(row + c) - m) - ls;
-      } else {                // fp32 arithmetic in torch's operation order: (x - max) - log(sum exp(x - max))
-        float m = -INFINITY;
-        for (int c = tid; c < V; c += kBeamThreads) m = fmaxf(m, (float)Elem<T>::load(row + c));
-        m = warp_max(m);
-        if (lane == 0) s_red[warp] = m;
-        __syncthreads();
-        m = s_red[0];
-        for (int w = 1; w < kBeamWarps; w++) m = fmaxf(m, s_red[w]);
-        __syncthreads();
-        float sum = 0.f;
-        for (int c = tid; c < V; c += kBeamThreads) sum += expf((float)Elem<T>::load(row + c) - m);
-        sum = warp_sum(sum);
-        if (lane == 0) s_red[warp] = sum;
-        __syncthreads();
-        sum = 0.f;
-        for (int w = 0; w < kBeamWarps; w++) sum += s_red[w];
-        const float ls = logf(sum);
-        for (int c = tid; c < V; c += kBeamThreads) {
-          float v = ((float)Elem<T>::load(row + c) - m) - ls;
-          if (sizeof(T) == 2) { T r; Elem<T>::store(&r, v); v = Elem<T>::get(r); }   // torch returns the input dtype
-          S.lp[c] = (double)v;
-        }
+    if (use_pre) {
+#pragma unroll
+      for (int k = 0; k < kBeamPre; k++) { const int c = tid + k * kBeamThreads; if (c < V) raw[c] = pre[k]; }
+      if (t + 1 < Ti) {
+#pragma unroll
+        for (int k = 0; k < kBeamPre; k++) { const int c = tid + k * kBeamThreads; if (c < V) pre[k] = (raw_t)Elem<T>::load(row + p.st + c); }
       }
     } else {
-      for (int c = tid; c < V; c += kBeamThreads) S.lp[c] = (double)Elem<T>::load(row + c);
+      for (int c = tid; c < V; c += kBeamThreads) raw[c] = (raw_t)Elem<T>::load(row + c);
     }
     for (int i = tid; i < W * VW; i += kBeamThreads) S.bitmap[i] = 0u;
+    if (tid == 0) { s_excl = 0; s_done = 0; s_kmax = 0ull; s_kmin = ~0ull; s_nz2 = 0; }
+    __syncthreads();
+    // ---- log-probabilities (decoders/ctc_decoder.py:95-97 when the input is raw logits): every warp reduces the whole row
+    //      on its own (same order, same result) so that no block-wide reduction sits on the chain -------------------------------
+    if (p.from_logits) {
+      raw_t m = -INFINITY;
+      for (int c = lane; c < V; c += 32) m = raw[c] > m ? raw[c] : m;
+      m = warp_max(m);
+      raw_t sum = 0;
+      if (sizeof(raw_t) == 8) { for (int c = lane; c < V; c += 32) sum += (raw_t)exp((double)raw[c] - (double)m); }
+      else { for (int c = lane; c < V; c += 32) sum += (raw_t)expf((float)raw[c] - (float)m); }
+      sum = warp_sum(sum);
+      const raw_t ls = sizeof(raw_t) == 8 ? (raw_t)log((double)sum) : (raw_t)logf((float)sum);
+      for (int c = tid; c < V; c += kBeamThreads) {
+        raw_t v = (raw[c] - m) - ls;   // torch's operation order
+        if (sizeof(T) == 2) { T r; Elem<T>::store(&r, (float)v); v = (raw_t)Elem<T>::get(r); }   // torch returns the input dtype
+        S.lp[c] = (double)v;
+      }
+    } else {
+      for (int c = tid; c < V; c += kBeamThreads) S.lp[c] = (double)raw[c];
+    }
     __syncthreads();
 
     // ---- phase A: every member's own update (:372-376, :383-385) ----------------------------------------------
@@ -195,84 +203,122 @@ __global__ void __launch_bounds__(kBeamThreads) ctc_beam_kernel(const BeamParams
       const double pbv = C.pb[s], pnbv = C.pnb[s];
       const double full = beam_lse(pnbv, pbv);                       // get_prev_full_prob (:331-333)
       S.full[s] = full;
-      S.npb[s] = beam_lse(-INFINITY, __dadd_rn(S.lp[p.blank], full));
+      S.npb[s] = __dadd_rn(S.lp[p.blank], full);                     // log_sum_exp(-inf, x) = x
       const int last = C.last[s];
-      S.npnb[s] = last >= 0 ? beam_lse(-INFINITY, __dadd_rn(S.lp[last], pnbv)) : -INFINITY;
+      S.npnb[s] = last >= 0 ? __dadd_rn(S.lp[last], pnbv) : -INFINITY;
       const int nws = C.nw[s];
-      S.nwx[s] = nws + ((nws == 0 || last == p.space) ? 1 : 0);      // :252-257 for a symbol other than space
+      const int nwx = nws + ((nws == 0 || last == p.space) ? 1 : 0); // :252-257 for a symbol other than space
+      S.nwx[s] = nwx;
+      S.penx[s] = __dmul_rn((double)nwx, p.wip); S.pens[s] = __dmul_rn((double)nws, p.wip);
     }
     __syncthreads();
-    // ---- phase B: living children (:244-246): merge into a member of the beam, or swallow --------------------
+    // ---- phase B: extensions that find a living prefix (:244-246): a member of the beam takes the mass, a pruned prefix
+    //      that a descendant keeps alive swallows it ---------------------------------------------------------------------------
     if (tid < W) {
-      const int s = tid, pn = C.node[s], last = C.last[s];
-      int prev = -1;
-      int z = nodes[pn].first_child;
-      while (z >= 0) {
-        const BeamNode zn = nodes[z];
-        if (zn.refs <= 0) {                      // expired weak_ptr: unlink
-          if (prev < 0) nodes[pn].first_child = zn.next_sib; else nodes[prev].next_sib = zn.next_sib;
-        } else {
-          const int c = zn.chr;
-          atomicOr(&S.bitmap[s * VW + (c >> 5)], 1u << (c & 31));
-          if (zn.slot >= 0) S.npnb[zn.slot] = beam_lse(S.npnb[zn.slot], ext_value(S, C, s, c, last));
-          prev = z;
-        }
-        z = zn.next_sib;
+      const int sp = C.pslot[tid];
+      if (sp >= 0) {
+        const int c = C.last[tid];
+        atomicOr(&S.bitmap[sp * VW + (c >> 5)], 1u << (c & 31));
+        S.npnb[tid] = beam_lse(S.npnb[tid], BEAM_EXT_VALUE(c, C.last[sp], C.pb[sp], S.full[sp]));
       }
     }
-    if (tid == 0) { s_total = 0; s_done = 0; }
+    for (int i = tid; i < nz; i += kBeamThreads) atomicOr(&S.bitmap[C.zp[i] * VW + (C.zc[i] >> 5)], 1u << (C.zc[i] & 31));
     __syncthreads();
-    // ---- phase C: member scores; how many prefixes are there after this frame (:392-399) ----------------------
+    // ---- phase C: scores of the members and of the fresh extensions; how many prefixes are there now (:392-399) ------
     if (tid < W) S.mkey[tid] = beam_key(beam_score(beam_lse(S.npnb[tid], S.npb[tid]), C.nw[tid], p.wip));
     {
       int excl = 0;
       for (int i = tid; i < W * VW; i += kBeamThreads) excl += __popc(S.bitmap[i]);
       excl = warp_sum(excl);
-      if (lane == 0 && excl) atomicAdd(&s_total, excl);
+      if (lane == 0 && excl) atomicAdd(&s_excl, excl);
+    }
+    if (CACHE) {
+      unsigned long long kmax = 0ull, kmin = ~0ull;
+      if (tid < W) {
+        // members take part in the range as well (mkey is this thread's own value)
+        kmax = S.mkey[tid]; kmin = kmax;
+      }
+      for (int s = warp; s < W; s += kBeamWarps) {
+        const int last = C.last[s];
+        const double base = S.full[s], baseb = C.pb[s];
+        const double penx = S.penx[s], pens = S.pens[s];
+        for (int c0 = 0; c0 < V; c0 += 32) {
+          const int c = c0 + lane;
+          if (c < V) {
+            unsigned long long k = 0ull;
+            if (c != p.blank && !((S.bitmap[s * VW + (c0 >> 5)] >> lane) & 1u)) {
+              const double v = BEAM_EXT_VALUE(c, last, baseb, base);
+              k = beam_key(__dsub_rn(__dadd_rn(v, 0.0), c == p.space ? pens : penx));
+              kmax = k > kmax ? k : kmax; kmin = k < kmin ? k : kmin;
+            }
+            S.kc[s * V + c] = k;
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, kmax, o), bq = __shfl_xor_sync(0xffffffffu, kmin, o);
+        kmax = a > kmax ? a : kmax; kmin = bq < kmin ? bq : kmin;
+      }
+      if (lane == 0) { atomicMax(&s_kmax, kmax); atomicMin(&s_kmin, kmin); }
     }
     __syncthreads();
-    const int total = W + W * (V - 1) - s_total;
-    // ---- phase D: radix select of the beam_width best ------------------------------------------------------------
+    const int total = W + W * (V - 1) - s_excl;
+    // ---- phase D: radix select of the beam_width best (8-bit digits from the highest byte in which the keys differ) -------
     unsigned long long thr = 0ull;
     int sh = 0, need = total;
     if (total > WB) {
       int remaining = WB;
       unsigned long long prefix = 0ull;
-      for (sh = 56; sh >= 0; sh -= 8) {
-        S.hist[tid] = 0u;                        // kBeamThreads == 256 bins
+      int sh0 = kBeamTopShift;
+      if (CACHE) {
+        const unsigned long long diff = s_kmax ^ s_kmin;
+        sh0 = diff ? ((63 - __clzll((long long)diff)) / kBeamDigit) * kBeamDigit : 0;
+        prefix = sh0 + kBeamDigit >= 64 ? 0ull : (s_kmax & (~0ull << (sh0 + kBeamDigit)));
+      }
+      for (sh = sh0; sh >= 0; sh -= kBeamDigit) {
+        for (int i = tid; i < kBeamBins; i += kBeamThreads) S.hist[i] = 0u;
         __syncthreads();
-        const unsigned long long pm = sh == 56 ? 0ull : (~0ull << (sh + 8));
+        const unsigned long long pm = sh + kBeamDigit >= 64 ? 0ull : (~0ull << (sh + kBeamDigit));
         if (tid < W) {
           const unsigned long long k = S.mkey[tid];
-          if ((k & pm) == (prefix & pm)) atomicAdd(&S.hist[(unsigned)(k >> sh) & 255u], 1u);
+          if ((k & pm) == (prefix & pm)) atomicAdd(&S.hist[(unsigned)(k >> sh) & (kBeamBins - 1)], 1u);
         }
-        for (int s = warp; s < W; s += kBeamWarps) {
-          const int last = C.last[s];
-          const double base = S.full[s], baseb = C.pb[s];
-          const double penx = __dmul_rn((double)S.nwx[s], p.wip), pens = __dmul_rn((double)C.nw[s], p.wip);
-          for (int c0 = 0; c0 < V; c0 += 32) {
-            const int c = c0 + lane;
-            bool valid = c < V && c != p.blank;
-            if (valid) valid = !((S.bitmap[s * VW + (c0 >> 5)] >> lane) & 1u);
-            unsigned long long k = 0ull;
-            if (valid) {
-              const double v = __dadd_rn(S.lp[c], c == last ? baseb : base);
-              k = beam_key(__dsub_rn(__dadd_rn(v, 0.0), c == p.space ? pens : penx));
-              valid = (k & pm) == (prefix & pm);
-            }
-            const unsigned d = (unsigned)(k >> sh) & 255u;
-            const unsigned act = __ballot_sync(0xffffffffu, valid);
-            if (valid) {
-              const unsigned m = __match_any_sync(act, d);
-              if (lane == __ffs(m) - 1) atomicAdd(&S.hist[d], (unsigned)__popc(m));
+        if (CACHE) {
+          for (int i = tid; i < W * V; i += kBeamThreads) {
+            const unsigned long long k = S.kc[i];
+            if (k && (k & pm) == (prefix & pm)) atomicAdd(&S.hist[(unsigned)(k >> sh) & (kBeamBins - 1)], 1u);
+          }
+        } else {
+          for (int s = warp; s < W; s += kBeamWarps) {
+            const int last = C.last[s];
+            const double base = S.full[s], baseb = C.pb[s];
+            const double penx = S.penx[s], pens = S.pens[s];
+            for (int c0 = 0; c0 < V; c0 += 32) {
+              const int c = c0 + lane;
+              bool valid = c < V && c != p.blank;
+              if (valid) valid = !((S.bitmap[s * VW + (c0 >> 5)] >> lane) & 1u);
+              unsigned long long k = 0ull;
+              if (valid) {
+                const double v = BEAM_EXT_VALUE(c, last, baseb, base);
+                k = beam_key(__dsub_rn(__dadd_rn(v, 0.0), c == p.space ? pens : penx));
+                valid = (k & pm) == (prefix & pm);
+              }
+              const unsigned d = (unsigned)(k >> sh) & (kBeamBins - 1);
+              const unsigned act = __ballot_sync(0xffffffffu, valid);
+              if (valid) {
+                const unsigned m = __match_any_sync(act, d);
+                if (lane == __ffs(m) - 1) atomicAdd(&S.hist[d], (unsigned)__popc(m));
+              }
             }
           }
         }
         __syncthreads();
         if (warp == 0) {                          // the bin that holds the remaining-th largest
-          unsigned h[8]; unsigned mine = 0;
+          constexpr int BPL = kBeamBins / 32;   // bins per lane
+          unsigned h[BPL]; unsigned mine = 0;
 #pragma unroll
-          for (int j = 0; j < 8; j++) { h[j] = S.hist[lane * 8 + j]; mine += h[j]; }
+          for (int j = 0; j < BPL; j++) { h[j] = S.hist[lane * BPL + j]; mine += h[j]; }
           unsigned above = 0;                     // entries in bins of higher lanes
           {
             unsigned v = mine;
@@ -282,11 +328,14 @@ __global__ void __launch_bounds__(kBeamThreads) ctc_beam_kernel(const BeamParams
           }
           const bool here = above < (unsigned)remaining && above + mine >= (unsigned)remaining;
           if (here) {
-            unsigned acc = above; int d = 7;
-            for (; d > 0; d--) { if (acc + h[d] >= (unsigned)remaining) break; acc += h[d]; }
+            unsigned acc = above, hd = h[0]; int d = 0;
+#pragma unroll
+            for (int j = BPL - 1; j > 0; j--) {     // no dynamic indexing of h[]: it stays in registers
+              if (d == 0) { if (acc + h[j] >= (unsigned)remaining) { d = j; hd = h[j]; } else acc += h[j]; }
+            }
             s_need = remaining - (int)acc;
-            s_thr = prefix | ((unsigned long long)(lane * 8 + d) << sh);
-            s_done = (h[d] == (unsigned)(remaining - (int)acc)) ? 1 : 0;
+            s_thr = prefix | ((unsigned long long)(lane * BPL + d) << sh);
+            s_done = (hd == (unsigned)(remaining - (int)acc)) ? 1 : 0;
             if (sh == 0 && !s_done) s_ties++;    // equal scores on both sides of the cut
           }
         }
@@ -299,25 +348,25 @@ __global__ void __launch_bounds__(kBeamThreads) ctc_beam_kernel(const BeamParams
     const unsigned long long tcls = thr >> sh;
     // ---- phase E: survivors per position group ---------------------------------------------------------------
     if (tid < W) {
-      const unsigned long long kc = S.mkey[tid] >> sh;
-      S.cgt[tid] = kc > tcls; S.ceq[tid] = kc == tcls;
+      const unsigned long long kq = S.mkey[tid] >> sh;
+      S.cgt[tid] = kq > tcls; S.ceq[tid] = kq == tcls;
     }
     for (int s = warp; s < W; s += kBeamWarps) {
       const int last = C.last[s];
       const double base = S.full[s], baseb = C.pb[s];
-      const double penx = __dmul_rn((double)S.nwx[s], p.wip), pens = __dmul_rn((double)C.nw[s], p.wip);
+      const double penx = S.penx[s], pens = S.pens[s];
       int ngt = 0, neq = 0;
       for (int c0 = 0; c0 < V; c0 += 32) {
         const int c = c0 + lane;
-        bool valid = c < V && c != p.blank;
-        if (valid) valid = !((S.bitmap[s * VW + (c0 >> 5)] >> lane) & 1u);
-        unsigned long long kc = 0ull;
-        if (valid) {
-          const double v = __dadd_rn(S.lp[c], c == last ? baseb : base);
-          kc = beam_key(__dsub_rn(__dadd_rn(v, 0.0), c == p.space ? pens : penx)) >> sh;
+        unsigned long long k = 0ull;
+        if (CACHE) { if (c < V) k = S.kc[s * V + c]; }
+        else if (c < V && c != p.blank && !((S.bitmap[s * VW + (c0 >> 5)] >> lane) & 1u)) {
+          const double v = BEAM_EXT_VALUE(c, last, baseb, base);
+          k = beam_key(__dsub_rn(__dadd_rn(v, 0.0), c == p.space ? pens : penx));
         }
-        ngt += __popc(__ballot_sync(0xffffffffu, valid && kc > tcls));
-        neq += __popc(__ballot_sync(0xffffffffu, valid && kc == tcls));
+        const unsigned long long kq = k >> sh;
+        ngt += __popc(__ballot_sync(0xffffffffu, k != 0ull && kq > tcls));
+        neq += __popc(__ballot_sync(0xffffffffu, k != 0ull && kq == tcls));
       }
       if (lane == 0) { S.cgt[W + s] = ngt; S.ceq[W + s] = neq; }
     }
@@ -341,52 +390,53 @@ __global__ void __launch_bounds__(kBeamThreads) ctc_beam_kernel(const BeamParams
     }
     __syncthreads();
     const int keepm = s_keepm, keepall = s_keepall, node0 = s_nodes;
+    // slot of member q after this frame's prune, -1 when it leaves the beam
+    auto new_slot = [&](int q) -> int {
+      const unsigned long long kq = S.mkey[q] >> sh;
+      const int eb = S.ceq[q];
+      return (kq > tcls || (kq == tcls && eb < need)) ? S.cgt[q] + min(eb, need) : -1;
+    };
     // ---- phase F: write the surviving list (next_step, :397) --------------------------------------------------
     bool dropped = false;
     if (tid < W) {
       const int s = tid;
-      const unsigned long long kc = S.mkey[s] >> sh;
-      const int gb = S.cgt[s], eb = S.ceq[s];
-      const bool keep = kc > tcls || (kc == tcls && eb < need);
-      const int n = C.node[s];
-      if (keep) {
-        const int ns = gb + min(eb, need);
-        N.node[ns] = n; N.last[ns] = C.last[s]; N.nw[ns] = C.nw[s]; N.dep[ns] = C.dep[s];
+      const int ns = new_slot(s);
+      if (ns >= 0) {
+        N.node[ns] = C.node[s]; N.par[ns] = C.par[s]; N.last[ns] = C.last[s]; N.nw[ns] = C.nw[s]; N.dep[ns] = C.dep[s];
         N.pb[ns] = S.npb[s]; N.pnb[ns] = S.npnb[s];
-        nodes[n].slot = ns;
+        const int sp = C.pslot[s];
+        N.pslot[ns] = sp >= 0 ? new_slot(sp) : -1;
       } else {
-        nodes[n].slot = -1;
         dropped = true;
       }
     }
     for (int s = warp; s < W; s += kBeamWarps) {
       const int last = C.last[s];
       const double base = S.full[s], baseb = C.pb[s];
-      const double penx = __dmul_rn((double)S.nwx[s], p.wip), pens = __dmul_rn((double)C.nw[s], p.wip);
+      const double penx = S.penx[s], pens = S.pens[s];
       int gb = S.cgt[W + s], eb = S.ceq[W + s];
       const int pn = C.node[s], pd = C.dep[s];
+      const int psl = new_slot(s);
       for (int c0 = 0; c0 < V; c0 += 32) {
         const int c = c0 + lane;
-        bool valid = c < V && c != p.blank;
-        if (valid) valid = !((S.bitmap[s * VW + (c0 >> 5)] >> lane) & 1u);
-        unsigned long long kc = 0ull;
-        double v = 0.0;
-        if (valid) {
-          v = __dadd_rn(S.lp[c], c == last ? baseb : base);
-          kc = beam_key(__dsub_rn(__dadd_rn(v, 0.0), c == p.space ? pens : penx)) >> sh;
+        unsigned long long k = 0ull;
+        if (CACHE) { if (c < V) k = S.kc[s * V + c]; }
+        else if (c < V && c != p.blank && !((S.bitmap[s * VW + (c0 >> 5)] >> lane) & 1u)) {
+          const double v = BEAM_EXT_VALUE(c, last, baseb, base);
+          k = beam_key(__dsub_rn(__dadd_rn(v, 0.0), c == p.space ? pens : penx));
         }
-        const bool isgt = valid && kc > tcls, iseq = valid && kc == tcls;
+        const unsigned long long kq = k >> sh;
+        const bool isgt = k != 0ull && kq > tcls, iseq = k != 0ull && kq == tcls;
         const unsigned mg = __ballot_sync(0xffffffffu, isgt), me = __ballot_sync(0xffffffffu, iseq);
         const unsigned below = (1u << lane) - 1u;
         const int g = gb + __popc(mg & below), e = eb + __popc(me & below);
         if (isgt || (iseq && e < need)) {
           const int ns = g + min(e, need);
           const int id = node0 + (ns - keepm);
-          N.node[ns] = id; N.last[ns] = c; N.dep[ns] = pd + 1;
+          N.node[ns] = id; N.par[ns] = pn; N.last[ns] = c; N.dep[ns] = pd + 1; N.pslot[ns] = psl;
           N.nw[ns] = c == p.space ? C.nw[s] : S.nwx[s];
-          N.pb[ns] = -INFINITY; N.pnb[ns] = beam_lse(-INFINITY, v);
-          BeamNode r; r.parent = pn; r.chr = c; r.refs = 1; r.slot = ns; r.depth = pd + 1; r.pad = 0; r.first_child = -1;
-          r.next_sib = atomicExch(&nodes[pn].first_child, id);
+          N.pb[ns] = -INFINITY; N.pnb[ns] = BEAM_EXT_VALUE(c, last, baseb, base);
+          BeamNode r; r.parent = pn; r.chr = c; r.refs = 1; r.depth = pd + 1;
           nodes[id] = r;
           atomicAdd(&nodes[pn].refs, 1);
         }
@@ -396,16 +446,35 @@ __global__ void __launch_bounds__(kBeamThreads) ctc_beam_kernel(const BeamParams
     __syncthreads();
     // ---- phase G: members that left the beam release their node; a node nobody holds releases its parent --------
     if (dropped) {
-      int n = C.node[tid];
-      while (n >= 0) {
+      int n = C.node[tid], par = C.par[tid];
+      while (true) {
         const int r = atomicSub(&nodes[n].refs, 1) - 1;
-        if (r > 0) break;
-        n = nodes[n].parent;
+        if (r > 0 || par < 0) break;
+        n = par;
+        par = __ldcg(&nodes[n].parent);
       }
     }
-    if (tid == 0) { s_W = keepall; s_nodes = node0 + (keepall - keepm); }
     __syncthreads();
+    // ---- phase H: the pruned prefixes that block an extension of a member next frame: still alive, parent still in the beam ---
+    for (int i = tid; i < nz; i += kBeamThreads) {
+      const int np = new_slot(C.zp[i]);
+      if (np >= 0 && __ldcg(&nodes[C.zn[i]].refs) > 0) {
+        const int o = atomicAdd(&s_nz2, 1);
+        if (o < WB) { N.zn[o] = C.zn[i]; N.zp[o] = np; N.zc[o] = C.zc[i]; } else s_ovf = 1;
+      }
+    }
+    if (dropped) {
+      const int sp = C.pslot[tid];
+      const int np = sp >= 0 ? new_slot(sp) : -1;
+      if (np >= 0 && __ldcg(&nodes[C.node[tid]].refs) > 0) {
+        const int o = atomicAdd(&s_nz2, 1);
+        if (o < WB) { N.zn[o] = C.node[tid]; N.zp[o] = np; N.zc[o] = C.last[tid]; } else s_ovf = 1;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) { s_W = keepall; s_nodes = node0 + (keepall - keepm); s_nz = min(s_nz2, WB); }
     { const BeamBuf tmp = C; C = N; N = tmp; }
+    __syncthreads();
   }
 
   // ---- the best prefix (:413-419) and its symbols (get_sentence, :225-239) -----------------------------------------
@@ -435,7 +504,7 @@ __global__ void __launch_bounds__(kBeamThreads) ctc_beam_kernel(const BeamParams
         for (int i = depth - 1; i >= 0; i--) { const BeamNode q = nodes[n]; out[i] = q.chr; n = q.parent; }
       }
       p.decoded_len[b] = len;
-      if (p.ties) p.ties[b] = s_ties;
+      if (p.ties) p.ties[b] = s_ovf ? -1 : s_ties;
       s_need = len;
     }
   }
@@ -443,19 +512,22 @@ __global__ void __launch_bounds__(kBeamThreads) ctc_beam_kernel(const BeamParams
   for (int k = s_need + tid; k < p.T; k += kBeamThreads) out[k] = 0;
 }
 
-size_t beam_smem_bytes(int V, int WB) {
+size_t beam_smem_bytes(int V, int WB, bool cache) {
   auto a16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
   const int VW = (V + 31) >> 5, Vp = (V + 1) & ~1;
-  size_t n = a16(sizeof(double) * Vp);
+  size_t n = 2 * a16(sizeof(double) * Vp);   // lp, raw
   n += 4 * a16(8 * (size_t)WB);        // pb, pnb x 2
   n += 4 * a16(8 * (size_t)WB);        // full, npb, npnb, mkey
-  n += 8 * a16(4 * (size_t)WB);        // node, last, nw, dep x 2
+  n += 18 * a16(4 * (size_t)WB);       // node, par, last, nw, dep, pslot, zn, zp, zc x 2
   n += a16(4 * (size_t)WB);            // nwx
   n += 2 * a16(4 * 2 * (size_t)WB);    // cgt, ceq
   n += a16((size_t)4 * WB * VW);
-  n += a16(4 * 256);
+  n += a16(4 * (size_t)kBeamBins) + 2 * a16(8 * (size_t)WB);   // hist, penx, pens
+  if (cache) n += a16((size_t)8 * WB * V);
   return n;
 }
+
+bool beam_cached(int V, int WB) { return (long long)V * WB <= kBeamKeyCache; }
 
 }  // namespace
 
@@ -465,7 +537,8 @@ size_t beam_workspace_bytes(const e2e_ctc_desc& d, int beam_width) {
 }
 
 bool beam_supported(const e2e_ctc_desc& d, int beam_width) {
-  return beam_width >= 1 && beam_width <= kBeamThreads && beam_smem_bytes(d.alphabet, beam_width) <= 200 * 1024;
+  return beam_width >= 1 && beam_width <= kBeamMaxWidth &&
+         beam_smem_bytes(d.alphabet, beam_width, beam_cached(d.alphabet, beam_width)) <= 200 * 1024;
 }
 
 int launch_beam(const e2e_ctc_desc& d, int beam_width, int space_idx, double wip, const void* logits, const void* in_len,
@@ -479,12 +552,22 @@ int launch_beam(const e2e_ctc_desc& d, int beam_width, int space_idx, double wip
   p.node_cap = (long long)d.max_frames * beam_width + 1;
   p.B = d.batch; p.T = d.max_frames; p.V = d.alphabet; p.blank = d.blank_idx; p.beam = beam_width; p.space = space_idx;
   p.from_logits = d.from_logits; p.wip = wip;
-  const size_t smem = beam_smem_bytes(d.alphabet, beam_width);
+  const bool cache = beam_cached(d.alphabet, beam_width);
+  const size_t smem = beam_smem_bytes(d.alphabet, beam_width, cache);
+  int dev = 0, sms = 148;
+  E2E_CUDA_TRY(cudaGetDevice(&dev));
+  E2E_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const bool wide = d.batch <= sms;
   KernelTimer timer(kKernelBeam, s);
+#define E2E_K8_(TYPE, CACHE_, NT_)                                                                            \
+  do {                                                                                                       \
+    E2E_CUDA_TRY(cudaFuncSetAttribute(ctc_beam_kernel<TYPE, CACHE_, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    ctc_beam_kernel<TYPE, CACHE_, NT_><<<(unsigned)d.batch, NT_, smem, s>>>(p);                              \
+  } while (0)
 #define E2E_K8(TYPE)                                                                                         \
   do {                                                                                                       \
-    E2E_CUDA_TRY(cudaFuncSetAttribute(ctc_beam_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    ctc_beam_kernel<TYPE><<<(unsigned)d.batch, kBeamThreads, smem, s>>>(p);                                  \
+    if (cache) { if (wide) E2E_K8_(TYPE, true, 512); else E2E_K8_(TYPE, true, 256); }                        \
+    else { if (wide) E2E_K8_(TYPE, false, 512); else E2E_K8_(TYPE, false, 256); }                            \
   } while (0)
   switch (d.dtype) {
     case E2E_F32: E2E_K8(float); break;
@@ -494,6 +577,7 @@ int launch_beam(const e2e_ctc_desc& d, int beam_width, int space_idx, double wip
     default: set_error("beam: unsupported dtype %d", d.dtype); return E2E_ERR_INVALID_ARGUMENT;
   }
 #undef E2E_K8
+#undef E2E_K8_
   E2E_CUDA_TRY(cudaGetLastError());
   return E2E_OK;
 }
