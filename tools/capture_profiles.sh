@@ -36,6 +36,26 @@ if [ "$what" = "ncu" ] || [ "$what" = "all" ]; then
   cap ncu_viterbi_c2   ctc_viterbi_kernel   1 python tools/run_one.py c2 2 0 --align
   cap ncu_noblank_c2   ctc_noblank_kernel   1 python tools/run_one.py c2 2 0 --noblank
   cap ncu_general_c1   ctc_fused_kernel     2 python tools/run_one.py c1 4
+  cap ncu_beam_c2      ctc_beam_kernel      1 python tools/beam_probe.py c2 100 1
+fi
+if [ "$what" = "beam" ]; then         # the prefix-beam-search kernel (added late in round 2)
+  cap() {
+    local name=$1 regex=$2 skip=$3; shift 3
+    $NCU --set full --import-source on -k "regex:$regex" -s $skip -c 1 -f -o $out/$name "$@" > $out/$name.log 2>&1
+    if [ -f $out/$name.ncu-rep ]; then
+      ncu -i $out/$name.ncu-rep --page raw --csv > $out/$name.raw.csv 2>/dev/null
+      ncu -i $out/$name.ncu-rep --page source --csv --print-source cuda,sass > $out/$name.source.csv 2>/dev/null
+      python tools/ncu_summary.py $out/$name.raw.csv > $out/$name.summary.txt 2>&1
+      python tools/ncu_lines.py $out/$name.source.csv 30 > $out/$name.lines.txt 2>&1
+      rm -f $out/$name.source.csv $out/$name.ncu-rep $out/$name.raw.csv
+    fi
+  }
+  cap ncu_beam_c2      ctc_beam_kernel      1 python tools/beam_probe.py c2 100 1
+  cap ncu_beam_c4      ctc_beam_kernel      1 python tools/beam_probe.py c4 100 1
+  for tool in memcheck racecheck synccheck; do
+    timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/beam_probe.py c1 100 1 > $out/san_${tool}_beam_c1.log 2>&1
+    tail -2 $out/san_${tool}_beam_c1.log
+  done
 fi
 if [ "$what" = "refresh" ]; then      # kernels changed after the first capture of the round
   NCUO=$NCU
