@@ -164,6 +164,10 @@ static bool make_sweep_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   p->off_status = off; off += 256;
   p->off_meet = off;
   p->off_flags = off; off += align256((size_t)d.batch * 4);
+  // Wide lattices run four CTAs per SM; a batch of several waves ends with a tail of half-empty SMs unless the long
+  // utterances go first (the hardware hands out CTAs in index order): c5 (B=2048) 11.7 -> see DESIGN.md
+  p->off_order = 0;
+  if (K >= 16 && d.batch > 4 * 148) { p->off_order = off; off += align256((size_t)d.batch * 4); }
   p->off_stats = off; off += p->dense ? 0 : align256(rows * (f64 ? 16 : 8));
   p->off_stash = off; off += align256(rows * 32 * p->words * 4);
   p->off_post = off; off += p->dense ? 0 : align256(rows * p->post_stride * 4);

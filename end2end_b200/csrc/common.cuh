@@ -33,6 +33,9 @@ struct SweepLayout {
 #ifndef E2E_SWEEP_MINBLK
 #define E2E_SWEEP_MINBLK 7
 #endif
+#ifndef E2E_SWEEP_WIDE_MINBLK
+#define E2E_SWEEP_WIDE_MINBLK 1
+#endif
 constexpr int kSweepPFSmall = E2E_SWEEP_PF_SMALL;
 
 constexpr int kWaveCF = 8;       // wave kernel: frames per hand-off chunk
@@ -90,6 +93,7 @@ struct LossPlan {
   size_t smem;      // dynamic shared memory of the lattice kernel
   // byte offsets into the workspace
   size_t off_status, off_meet, off_flags, off_stats, off_stash, off_post, off_emis, total;
+  size_t off_order; // sweep, multi-wave batches of wide lattices: utterance indices by falling frame count (0: launch in index order)
   int emis_stride;  // general kernel, gather mode: doubles per frame of the compact emission rows K1 writes (0: none)
 };
 
@@ -104,7 +108,7 @@ constexpr int kFlagInfeasible = 1, kFlagInvalid = 2;
 void set_error(const char* fmt, ...);
 
 // Launch accounting + optional per-kernel device timing (CUDA events on the launching stream).
-enum { kKernelRowStats = 0, kKernelLattice, kKernelGrad, kKernelReduce, kKernelArgmax, kKernelCollapse, kKernelScale, kKernelViterbi, kKernelNoBlank, kKernelBeam, kNumKernels };
+enum { kKernelRowStats = 0, kKernelLattice, kKernelGrad, kKernelReduce, kKernelArgmax, kKernelCollapse, kKernelScale, kKernelViterbi, kKernelNoBlank, kKernelBeam, kKernelOrder, kNumKernels };
 void launch_begin(int kind, cudaStream_t s);
 void launch_end(int kind, cudaStream_t s);
 struct KernelTimer {   // brackets exactly one kernel launch

@@ -26,6 +26,24 @@ static int launch_sweep_a(int K, bool f64, const SweepParams& sp, size_t smem, c
   return E2E_ERR_UNSUPPORTED;
 }
 
+// Utterance indices by falling frame count (ties by index): order[rank] = b.  One thread per utterance counts the
+// utterances that go before it; lengths outside [1, T] (rejected later by the lattice kernel) sort as 0.
+__global__ void __launch_bounds__(256) ctc_order_kernel(const void* in_len, int is64, int B, int T, int* __restrict__ order) {
+  __shared__ int tile[256];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  auto key = [&](int j) { const long long v = load_index(in_len, is64, j); return (v < 1 || v > T) ? 0 : (int)v; };
+  const int mine = i < B ? key(i) : 0;
+  int rank = 0;
+  for (int j0 = 0; j0 < B; j0 += 256) {
+    __syncthreads();
+    tile[threadIdx.x] = j0 + threadIdx.x < B ? key(j0 + threadIdx.x) : -1;
+    __syncthreads();
+    const int n = min(256, B - j0);
+    for (int q = 0; q < n; q++) { const int k = tile[q]; rank += (k > mine) || (k == mine && j0 + q < i); }
+  }
+  if (i < B) order[rank] = i;
+}
+
 int launch_sweep(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, const void* targets,
                  const void* in_len, const void* tgt_len, void* losses, void* grads, double scale, char* ws,
                  cudaStream_t s) {
@@ -41,6 +59,14 @@ int launch_sweep(const e2e_ctc_desc& d, const LossPlan& p, const void* logits, c
   sp.status = reinterpret_cast<int*>(ws + p.off_status);
   sp.flags = reinterpret_cast<int*>(ws + p.off_flags);
   sp.stash = reinterpret_cast<uint32_t*>(ws + p.off_stash);
+  sp.order = nullptr;
+  if (p.off_order) {
+    int* order = reinterpret_cast<int*>(ws + p.off_order);
+    KernelTimer timer(kKernelOrder, s);
+    ctc_order_kernel<<<(unsigned)((d.batch + 255) / 256), 256, 0, s>>>(in_len, d.lengths_itype == E2E_I64, d.batch, d.max_frames, order);
+    E2E_CUDA_TRY(cudaGetLastError());
+    sp.order = order;
+  }
   sp.post = reinterpret_cast<float*>(ws + p.off_post);
   sp.dense = p.dense; sp.post_stride = p.post_stride; sp.cells = p.cells;
   sp.cf = p.sw.cf; sp.es = p.sw.es; sp.rawrow = p.sw.rawrow; sp.vpad = p.sw.vpad;

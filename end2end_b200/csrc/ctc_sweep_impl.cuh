@@ -46,6 +46,7 @@ struct SweepParams {
   int B, T, V, Lmax, blank, from_logits;
   void* losses;
   int* status; int* flags;
+  const int* order;  // [B] utterance handled by each CTA (null: its own index)
   uint32_t* stash;   // [B*T][32][WORDS]  first-half lattice state
   float* post;       // gather mode: [B*T][post_stride] compact posteriors (labels..., blank total at cells/2)
   int dense, post_stride, cells;
@@ -369,8 +370,16 @@ __device__ void run_sweep(const SweepParams& p, unsigned char* smem, int b, int 
   const int nstore = BWD ? (Ti - tm) : tm;   // frames this sweep stores; the rest it combines
   uint32_t* const stash_u = p.stash + (size_t)b * p.T * ROWW + (size_t)lane * WORDS;   // + t*ROWW
   auto frame_t = [&](int i) { return BWD ? (Ti - 1 - i) : i; };
+  // The reference's window (ctc_loss.cpp:44-45): at frame t only cells [max(0, S - 2(T - t)), min(2t + 2, S)) can carry
+  // alpha * beta != 0 -- below it beta is exactly 0, above it alpha is.  A lane whose K cells all lie outside the window
+  // neither stores its part of the row nor fetches the other sweep's part (the combine step takes zeros): for long
+  // utterances about half of the stash traffic.
+  // (Wide variants only: with few cells per lane the stash is small and the test costs more than it saves -- c3, K = 4:
+  // 173 -> 188 us with it, c5, K = 40: 13.7 -> 11.9 ms.)
+  constexpr bool kBand = K >= 16;
+  auto lane_live = [&](int t) { return !kBand || (s0 < min(2 * t + 2, S) && s0 + K > S - 2 * (Ti - t)); };
   auto prefetch = [&](int i2) {   // the other sweep's stored row of iteration i2 -> staging slot i2 % PF
-    if (i2 < Ti) {
+    if (i2 < Ti && lane_live(frame_t(i2))) {
       uint32_t* dst = stage + (size_t)(i2 % PF) * ROWW;
       const uint32_t* src = stash_u + (size_t)frame_t(i2) * ROWW;
 #pragma unroll
@@ -461,9 +470,11 @@ __device__ void run_sweep(const SweepParams& p, unsigned char* smem, int b, int 
       wds[K] = (uint32_t)s.e;
 #pragma unroll
       for (int j = K + 1; j < WORDS; j++) wds[j] = 0u;
+      if (lane_live(t)) {
 #pragma unroll
-      for (int u = 0; u < WORDS / 4; u++)
-        reinterpret_cast<uint4*>(dst)[u] = make_uint4(wds[4 * u], wds[4 * u + 1], wds[4 * u + 2], wds[4 * u + 3]);
+        for (int u = 0; u < WORDS / 4; u++)
+          reinterpret_cast<uint4*>(dst)[u] = make_uint4(wds[4 * u], wds[4 * u + 1], wds[4 * u + 2], wds[4 * u + 3]);
+      }
       if (i == nstore - 1) {
         // meet: publish my stored rows, wait for the other sweep's (both warps pass here exactly once)
         __threadfence();
@@ -480,9 +491,10 @@ __device__ void run_sweep(const SweepParams& p, unsigned char* smem, int b, int 
       sw_cp_async_wait<PF - 1>();
       const uint32_t* orow = stage + (size_t)(i % PF) * ROWW;
       uint32_t ow[WORDS];
+      const bool olive = lane_live(t);   // the other sweep stored this lane's part of frame t
 #pragma unroll
       for (int u = 0; u < WORDS / 4; u++) {
-        const uint4 q = reinterpret_cast<const uint4*>(orow)[u];
+        const uint4 q = olive ? reinterpret_cast<const uint4*>(orow)[u] : make_uint4(0u, 0u, 0u, 0u);
         ow[4 * u] = q.x; ow[4 * u + 1] = q.y; ow[4 * u + 2] = q.z; ow[4 * u + 3] = q.w;
       }
       prefetch(i + PF);
@@ -615,7 +627,7 @@ __device__ void run_sweep(const SweepParams& p, unsigned char* smem, int b, int 
 
 // ---- kernel -----------------------------------------------------------------------------------
 template <int K, bool F64>
-__global__ void __launch_bounds__(64, K <= 8 ? E2E_SWEEP_MINBLK : 1)
+__global__ void __launch_bounds__(64, K <= 8 ? E2E_SWEEP_MINBLK : (K >= 32 ? E2E_SWEEP_WIDE_MINBLK : 1))
 ctc_sweep_kernel(const SweepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using ET = typename std::conditional<F64, double, float>::type;
@@ -623,7 +635,7 @@ ctc_sweep_kernel(const SweepParams p) {
   int* lab = reinterpret_cast<int*>(smem_raw + p.off_lab);
   __shared__ int misc[4];
 
-  const int b = blockIdx.x;
+  const int b = p.order ? p.order[blockIdx.x] : (int)blockIdx.x;
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
 
   const long long Ti_ll = load_index(p.in_len, p.len_is64, b);
