@@ -122,7 +122,7 @@ static bool make_sweep_plan(const e2e_ctc_desc& d, bool fused, LossPlan* p) {
   const int rowlen = p->dense ? d.alphabet : d.max_targets + 1;
   p->post_stride = p->cells / 2 + 4;
   p->vpad = p->dense ? ((d.alphabet + 1 + 3) & ~3) : 0;
-  const int H = K / 2, PF = K >= 24 ? 2 : kSweepPFSmall;
+  const int H = K / 2, PF = K >= 24 ? kSweepPFWide : kSweepPFSmall;
   const int et = f64 ? 8 : 4;
   const int esz = f64 ? 8 : (d.dtype == E2E_F32 ? 4 : 2);
   SweepLayout L;

@@ -36,7 +36,11 @@ struct SweepLayout {
 #ifndef E2E_SWEEP_WIDE_MINBLK
 #define E2E_SWEEP_WIDE_MINBLK 1
 #endif
+#ifndef E2E_SWEEP_PF_WIDE
+#define E2E_SWEEP_PF_WIDE 2
+#endif
 constexpr int kSweepPFSmall = E2E_SWEEP_PF_SMALL;
+constexpr int kSweepPFWide = E2E_SWEEP_PF_WIDE;
 
 constexpr int kWaveCF = 8;       // wave kernel: frames per hand-off chunk
 constexpr int kWaveRB = 32;      // boundary-slot ring depth (frames)

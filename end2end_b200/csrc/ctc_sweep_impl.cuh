@@ -81,7 +81,7 @@ template <int K> struct SweepCfg {
   static constexpr int H = K / 2;
   static constexpr int WORDS = (K + 1 + 3) & ~3;
   static constexpr int ROWW = 32 * WORDS;
-  static constexpr int PF = K >= 24 ? 2 : kSweepPFSmall;
+  static constexpr int PF = K >= 24 ? kSweepPFWide : kSweepPFSmall;
 };
 
 template <int K, typename ET>
