@@ -28,6 +28,8 @@
 //
 // Arithmetic: fp64 log-space with the reference's two-argument log_sum_exp (src/utils/math_utils.h:8-16) and the score
 // expression of :311-315 evaluated in its order without fused multiply-adds.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace e2e {
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
   constexpr int kBeamThreads = NT, kBeamWarps = NT / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned long long s_thr, s_kmax, s_kmin;
-  __shared__ int s_need, s_W, s_nodes, s_ties, s_excl, s_done, s_keepm, s_keepall, s_nz, s_nz2, s_ovf;
+  __shared__ int s_need, s_ties, s_excl, s_done, s_keepm, s_keepall, s_nz2, s_ovf;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int V = p.V, WB = p.beam, VW = (V + 31) >> 5, Vp = (V + 1) & ~1;
   using raw_t = typename Elem<T>::acc_t;   // float for 32/16-bit inputs, double for f64
@@ -149,33 +151,59 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
     BeamNode r; r.parent = -1; r.chr = -1; r.refs = 1; r.depth = 0;
     nodes[0] = r;
     C.node[0] = 0; C.par[0] = -1; C.last[0] = -1; C.nw[0] = 0; C.dep[0] = 0; C.pslot[0] = -1; C.pb[0] = 0.0; C.pnb[0] = -INFINITY;
-    s_W = 1; s_nodes = 1; s_ties = 0; s_nz = 0; s_ovf = 0;
+    s_ties = 0; s_ovf = 0; s_nz2 = 0;
   }
+  // The first kFront threads (8 warps) run the head of a frame -- staging the row, the log-softmax, the members' own
+  // updates -- synchronising among themselves on a named barrier.  With 512 threads the other half spends that time
+  // releasing the trie nodes of the members the PREVIOUS frame pruned (dependent atomics to L2: a fifth of the frame when
+  // it sat on the critical path); the two halves meet at one CTA-wide barrier before the blocked-extension list is rebuilt.
+  constexpr int kFront = 256;
+  constexpr int kCascOff = kBeamThreads >= 2 * kBeamMaxWidth ? kBeamMaxWidth : 0;   // thread kCascOff + u releases member u
+  auto front_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kFront) : "memory"); };
   raw_t pre[kBeamPre];
 #pragma unroll
   for (int k = 0; k < kBeamPre; k++) {
-    const int c = tid + k * kBeamThreads;
-    pre[k] = (use_pre && Ti > 0 && c < V) ? (raw_t)Elem<T>::load(x + c) : (raw_t)0;
+    const int c = tid + k * kFront;
+    pre[k] = (use_pre && Ti > 0 && tid < kFront && c < V) ? (raw_t)Elem<T>::load(x + c) : (raw_t)0;
   }
   __syncthreads();
 
+  int W = 1, n_nodes = 1, nz_prev = 0, W_prev = 0;
+  int casc_n = -1, casc_par = -1;                 // the node this thread releases at the top of the next frame
+  unsigned long long ptcls = 0ull; int psh = 0, pneed = 0;   // last frame's cut: slot of a member after that prune
+  auto prev_slot = [&](int q) -> int {
+    const unsigned long long kq = S.mkey[q] >> psh;
+    const int eb = S.ceq[q];
+    return (kq > ptcls || (kq == ptcls && eb < pneed)) ? S.cgt[q] + min(eb, pneed) : -1;
+  };
   for (int t = 0; t < Ti; t++) {
-    const int W = s_W, nz = s_nz;
-    // ---- the frame's row: staged from the registers it was prefetched into; the next frame's row is requested now ------
-    const T* row = x + (long long)t * p.st;
-    if (use_pre) {
-#pragma unroll
-      for (int k = 0; k < kBeamPre; k++) { const int c = tid + k * kBeamThreads; if (c < V) raw[c] = pre[k]; }
-      if (t + 1 < Ti) {
-#pragma unroll
-        for (int k = 0; k < kBeamPre; k++) { const int c = tid + k * kBeamThreads; if (c < V) pre[k] = (raw_t)Elem<T>::load(row + p.st + c); }
+    // ---- members that left the beam last frame release their node; a node nobody holds releases its parent (off the
+    //      critical path: see above) ----------------------------------------------------------------------------------------
+    if (casc_n >= 0) {
+      int n = casc_n, par = casc_par;
+      while (true) {
+        const int r = atomicSub(&nodes[n].refs, 1) - 1;
+        if (r > 0 || par < 0) break;
+        n = par;
+        par = __ldcg(&nodes[n].parent);
       }
-    } else {
-      for (int c = tid; c < V; c += kBeamThreads) raw[c] = (raw_t)Elem<T>::load(row + c);
     }
-    for (int i = tid; i < W * VW; i += kBeamThreads) S.bitmap[i] = 0u;
-    if (tid == 0) { s_excl = 0; s_done = 0; s_kmax = 0ull; s_kmin = ~0ull; s_nz2 = 0; }
-    __syncthreads();
+    if (tid < kFront) {
+      // ---- the frame's row: staged from the registers it was prefetched into; the next frame's row is requested now ----
+      const T* row = x + (long long)t * p.st;
+      if (use_pre) {
+#pragma unroll
+        for (int k = 0; k < kBeamPre; k++) { const int c = tid + k * kFront; if (c < V) raw[c] = pre[k]; }
+        if (t + 1 < Ti) {
+#pragma unroll
+          for (int k = 0; k < kBeamPre; k++) { const int c = tid + k * kFront; if (c < V) pre[k] = (raw_t)Elem<T>::load(row + p.st + c); }
+        }
+      } else {
+        for (int c = tid; c < V; c += kFront) raw[c] = (raw_t)Elem<T>::load(row + c);
+      }
+      for (int i = tid; i < W * VW; i += kFront) S.bitmap[i] = 0u;
+      if (tid == 0) { s_excl = 0; s_done = 0; s_kmax = 0ull; s_kmin = ~0ull; s_nz2 = 0; }
+      front_sync();
     // ---- log-probabilities (decoders/ctc_decoder.py:95-97 when the input is raw logits): every warp reduces the whole row
     //      on its own (same order, same result) so that no block-wide reduction sits on the chain -------------------------------
     if (p.from_logits) {
@@ -187,15 +215,15 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
       else { for (int c = lane; c < V; c += 32) sum += (raw_t)expf((float)raw[c] - (float)m); }
       sum = warp_sum(sum);
       const raw_t ls = sizeof(raw_t) == 8 ? (raw_t)log((double)sum) : (raw_t)logf((float)sum);
-      for (int c = tid; c < V; c += kBeamThreads) {
+      for (int c = tid; c < V; c += kFront) {
         raw_t v = (raw[c] - m) - ls;   // torch's operation order
         if (sizeof(T) == 2) { T r; Elem<T>::store(&r, (float)v); v = (raw_t)Elem<T>::get(r); }   // torch returns the input dtype
         S.lp[c] = (double)v;
       }
     } else {
-      for (int c = tid; c < V; c += kBeamThreads) S.lp[c] = (double)raw[c];
+      for (int c = tid; c < V; c += kFront) S.lp[c] = (double)raw[c];
     }
-    __syncthreads();
+    front_sync();
 
     // ---- phase A: every member's own update (:372-376, :383-385) ----------------------------------------------
     if (tid < W) {
@@ -211,7 +239,28 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
       S.nwx[s] = nwx;
       S.penx[s] = __dmul_rn((double)nwx, p.wip); S.pens[s] = __dmul_rn((double)nws, p.wip);
     }
+    }   // front threads
+    __syncthreads();   // the members' updates are done; so are last frame's releases
+    // ---- the pruned prefixes that block an extension of a member THIS frame: pruned last frame or earlier, still alive
+    //      (a descendant in the beam holds them), parent still in the beam.  N holds last frame's beam and list. ------------
+    for (int i = tid; i < nz_prev; i += kBeamThreads) {
+      const int np = prev_slot(N.zp[i]);
+      if (np >= 0 && __ldcg(&nodes[N.zn[i]].refs) > 0) {
+        const int o = atomicAdd(&s_nz2, 1);
+        if (o < WB) { C.zn[o] = N.zn[i]; C.zp[o] = np; C.zc[o] = N.zc[i]; } else s_ovf = 1;
+      }
+    }
+    for (int u = tid; u < W_prev; u += kBeamThreads) {
+      if (prev_slot(u) >= 0) continue;
+      const int sp = N.pslot[u];
+      const int np = sp >= 0 ? prev_slot(sp) : -1;
+      if (np >= 0 && __ldcg(&nodes[N.node[u]].refs) > 0) {
+        const int o = atomicAdd(&s_nz2, 1);
+        if (o < WB) { C.zn[o] = N.node[u]; C.zp[o] = np; C.zc[o] = N.last[u]; } else s_ovf = 1;
+      }
+    }
     __syncthreads();
+    const int nz = min(s_nz2, WB);
     // ---- phase B: extensions that find a living prefix (:244-246): a member of the beam takes the mass, a pruned prefix
     //      that a descendant keeps alive swallows it ---------------------------------------------------------------------------
     if (tid < W) {
@@ -389,7 +438,7 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
       if (lane == 0) s_keepall = run_gt + min(run_eq, need);
     }
     __syncthreads();
-    const int keepm = s_keepm, keepall = s_keepall, node0 = s_nodes;
+    const int keepm = s_keepm, keepall = s_keepall, node0 = n_nodes;
     // slot of member q after this frame's prune, -1 when it leaves the beam
     auto new_slot = [&](int q) -> int {
       const unsigned long long kq = S.mkey[q] >> sh;
@@ -397,7 +446,6 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
       return (kq > tcls || (kq == tcls && eb < need)) ? S.cgt[q] + min(eb, need) : -1;
     };
     // ---- phase F: write the surviving list (next_step, :397) --------------------------------------------------
-    bool dropped = false;
     if (tid < W) {
       const int s = tid;
       const int ns = new_slot(s);
@@ -406,8 +454,6 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
         N.pb[ns] = S.npb[s]; N.pnb[ns] = S.npnb[s];
         const int sp = C.pslot[s];
         N.pslot[ns] = sp >= 0 ? new_slot(sp) : -1;
-      } else {
-        dropped = true;
       }
     }
     for (int s = warp; s < W; s += kBeamWarps) {
@@ -444,41 +490,19 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
       }
     }
     __syncthreads();
-    // ---- phase G: members that left the beam release their node; a node nobody holds releases its parent --------
-    if (dropped) {
-      int n = C.node[tid], par = C.par[tid];
-      while (true) {
-        const int r = atomicSub(&nodes[n].refs, 1) - 1;
-        if (r > 0 || par < 0) break;
-        n = par;
-        par = __ldcg(&nodes[n].parent);
-      }
+    // ---- carried into the next frame: the nodes to release, this frame's cut (slot of a member after the prune) ------
+    {
+      const int u = tid - kCascOff;
+      casc_n = -1;
+      if (u >= 0 && u < W && new_slot(u) < 0) { casc_n = C.node[u]; casc_par = C.par[u]; }
     }
-    __syncthreads();
-    // ---- phase H: the pruned prefixes that block an extension of a member next frame: still alive, parent still in the beam ---
-    for (int i = tid; i < nz; i += kBeamThreads) {
-      const int np = new_slot(C.zp[i]);
-      if (np >= 0 && __ldcg(&nodes[C.zn[i]].refs) > 0) {
-        const int o = atomicAdd(&s_nz2, 1);
-        if (o < WB) { N.zn[o] = C.zn[i]; N.zp[o] = np; N.zc[o] = C.zc[i]; } else s_ovf = 1;
-      }
-    }
-    if (dropped) {
-      const int sp = C.pslot[tid];
-      const int np = sp >= 0 ? new_slot(sp) : -1;
-      if (np >= 0 && __ldcg(&nodes[C.node[tid]].refs) > 0) {
-        const int o = atomicAdd(&s_nz2, 1);
-        if (o < WB) { N.zn[o] = C.node[tid]; N.zp[o] = np; N.zc[o] = C.last[tid]; } else s_ovf = 1;
-      }
-    }
-    __syncthreads();
-    if (tid == 0) { s_W = keepall; s_nodes = node0 + (keepall - keepm); s_nz = min(s_nz2, WB); }
+    ptcls = tcls; psh = sh; pneed = need; nz_prev = nz; W_prev = W;
+    W = keepall; n_nodes = node0 + (keepall - keepm);
     { const BeamBuf tmp = C; C = N; N = tmp; }
-    __syncthreads();
   }
 
   // ---- the best prefix (:413-419) and its symbols (get_sentence, :225-239) -----------------------------------------
-  const int W = s_W;
+  __syncthreads();   // the last frame's tail still reads the member keys
   if (tid < W) S.mkey[tid] = beam_key(beam_score(beam_lse(C.pnb[tid], C.pb[tid]), C.nw[tid], p.wip));
   __syncthreads();
   long long* out = p.decoded + (long long)b * p.T;
@@ -557,7 +581,8 @@ int launch_beam(const e2e_ctc_desc& d, int beam_width, int space_idx, double wip
   int dev = 0, sms = 148;
   E2E_CUDA_TRY(cudaGetDevice(&dev));
   E2E_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const bool wide = d.batch <= sms;
+  static const int force_wide = []() { const char* v = getenv("E2E_CTC_BEAM_WIDE"); return (v && *v) ? atoi(v) : -1; }();   // experiments only
+  const bool wide = force_wide >= 0 ? force_wide != 0 : d.batch <= sms;
   KernelTimer timer(kKernelBeam, s);
 #define E2E_K8_(TYPE, CACHE_, NT_)                                                                            \
   do {                                                                                                       \

@@ -130,6 +130,19 @@ def test_beam_fused_log_softmax_dtypes_and_layouts():
     _check_vs_oracle(big, torch.tensor([40, 31]), 0, 100, after_logsoftmax=False)
 
 
+def test_beam_large_batch_variant():
+    """Batches beyond one CTA per SM run the 256-thread kernel (several CTAs per SM): same results."""
+    g = torch.Generator().manual_seed(10)
+    for V, beam, T, B in ((12, 16, 40, 170), (29, 100, 30, 150), (300, 64, 12, 160)):
+        lp = torch.log_softmax(torch.randn(B, T, V, generator=g) * 2.0, 2)
+        ll = torch.randint(T // 2, T + 1, (B,), generator=g)
+        dec = CTCDecoder(beam_width=beam, after_logsoftmax=True, blank_idx=0, wip=0.3)   # (the wrapper's default wip is 1.0)
+        res = dec.decode(lp.cuda(), ll)
+        port = oracle.beam_decode(lp, ll, beam_width=beam, after_logsoftmax=True, wip=0.3, prefer="port", return_ties=True)
+        assert _rows(res.decoded_targets, res.decoded_targets_lengths) == _rows(port[0], port[1])
+        assert torch.equal(dec._decoder.last_ties, port[3])
+
+
 def test_beam_full_size_c2():
     """BASELINE config 2 at its full batch (B=64, T=400, V=29), the reference's default beam of 100."""
     x, _, ll, _ = oracle.make_inputs(*oracle.CONFIGS["c2"][:6])
