@@ -160,13 +160,28 @@ ctc_grad_kernel(const GradParams p) {
 #pragma unroll
     for (int j = 0; j < PRE; j++) { const int i = j * 32 + lane; if (i < nvec) Vec16<T>::load(x + i * N, xr[j]); }
   }
+  // compact posterior row written by the lattice kernel's combiners: [label 0 .. label L-1 | ... | blank total].  Its
+  // values (<= 4 per lane up to 128 labels) are requested together with the row, ahead of the accumulator clear: the
+  // scatter below waited on these loads for 28 % of the kernel's samples
+  const float* post = p.post + row * p.post_stride;
+  constexpr int PK = 4;
+  float pv[PK];
+  const bool post_pre = Li <= 32 * PK;
+  if (post_pre) {
+#pragma unroll
+    for (int q = 0; q < PK; q++) { const int li = lane + 32 * q; pv[q] = li < Li ? __ldcg(post + li) : 0.f; }
+  }
+  const float pblank = lane == 0 ? __ldcg(post + p.cells / 2) : 0.f;
   float* acc = s_acc + (size_t)w * p.vstride;
   for (int v = lane * 4; v < p.vstride; v += 128) *reinterpret_cast<float4*>(acc + v) = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
-  // compact posterior row written by the lattice kernel's combiners: [label 0 .. label L-1 | ... | blank total]
-  const float* post = p.post + row * p.post_stride;
-  for (int li = lane; li < Li; li += 32) atomicAdd(&acc[s_lab[li]], __ldcg(post + li));
-  if (lane == 0) atomicAdd(&acc[p.blank], __ldcg(post + p.cells / 2));
+  if (post_pre) {
+#pragma unroll
+    for (int q = 0; q < PK; q++) { const int li = lane + 32 * q; if (li < Li) atomicAdd(&acc[s_lab[li]], pv[q]); }
+  } else {
+    for (int li = lane; li < Li; li += 32) atomicAdd(&acc[s_lab[li]], __ldcg(post + li));
+  }
+  if (lane == 0) atomicAdd(&acc[p.blank], pblank);
   __syncwarp();
 
   acc_t m = 0, ls = 0;
