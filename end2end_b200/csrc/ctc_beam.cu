@@ -13,6 +13,11 @@
 //     the frame's log-probability to a per-member base, recomputed wherever it is needed;
 //   * the beam_width best of the beam members + extensions are found by an MSB-first radix select on an order-preserving
 //     64-bit image of the fp64 score (8-bit digits, stops as soon as a digit bin holds exactly what is still needed);
+//   * large alphabets (beam x V beyond the key cache): for one member the extensions with an ordinary symbol rank by the
+//     symbol's log-probability alone, so only the beam_width + 2 most probable symbols of the frame (ties included; the
+//     member's own last symbol and the space score differently) plus the space can reach the beam_width best.  Their
+//     threshold comes from a radix select over the row, and every member is extended with that list only (c4, V = 1024:
+//     104 of 1023 symbols, 73 -> 14 ms); same results as without the filter;
 //   * survivors are compacted in position order (members in beam order, then extensions by (member, symbol)) with
 //     ballot / popc ranks and one scan over the per-member counts: bitwise reproducible.
 //
@@ -48,6 +53,8 @@ struct BeamParams {
   BeamNode* nodes;           // [B][node_cap]
   long long node_cap;
   int B, T, V, blank, beam, space, from_logits;
+  int prefilter;             // large alphabets: only the beam+2 most probable symbols of a frame (and the space) are extended
+  int kc_cap;                // keys the shared-memory cache holds (0: none)
   double wip;
 };
 
@@ -96,7 +103,9 @@ struct BeamSmem {
   unsigned* bitmap;      // [W][VW] extensions that are not fresh prefixes
   unsigned* hist;        // [kBeamBins]
   double *penx, *pens;   // word penalty of an extension with a symbol other than space / with the space
-  unsigned long long* kc;   // [W][V] keys of the extensions (0: none) when they fit
+  unsigned long long* kc;   // [W][nR] keys of the extensions (0: none) when they fit
+  int* rc;               // [nR] the symbols a member is extended with this frame, ascending (never the blank)
+  unsigned* rmask;       // [VW] the same set as a bit mask
 };
 
 // :381-390: a repeated character extends from the blank-ending mass only
@@ -109,7 +118,7 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
   constexpr int kBeamThreads = NT, kBeamWarps = NT / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned long long s_thr, s_kmax, s_kmin;
-  __shared__ int s_need, s_ties, s_excl, s_done, s_keepm, s_keepall, s_nz2, s_ovf;
+  __shared__ int s_need, s_ties, s_excl, s_done, s_keepm, s_keepall, s_nz2, s_ovf, s_nR, s_wcnt[8];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int V = p.V, WB = p.beam, VW = (V + 31) >> 5, Vp = (V + 1) & ~1;
   using raw_t = typename Elem<T>::acc_t;   // float for 32/16-bit inputs, double for f64
@@ -138,7 +147,9 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
     S.bitmap = reinterpret_cast<unsigned*>(take((size_t)4 * WB * VW));
     S.hist = reinterpret_cast<unsigned*>(take(4 * kBeamBins));
     S.penx = reinterpret_cast<double*>(take(8 * WB)); S.pens = reinterpret_cast<double*>(take(8 * WB));
-    S.kc = reinterpret_cast<unsigned long long*>(take(CACHE ? (size_t)8 * WB * V : 0));
+    S.rc = reinterpret_cast<int*>(take(4 * (size_t)V));
+    S.rmask = reinterpret_cast<unsigned*>(take(4 * (size_t)VW));
+    S.kc = reinterpret_cast<unsigned long long*>(take(CACHE ? (size_t)8 * p.kc_cap : 0));
   }
 
   long long Ti_ll = p.in_len ? load_index(p.in_len, p.len_is64, b) : (long long)p.T;
@@ -160,6 +171,13 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
   constexpr int kFront = 256;
   constexpr int kCascOff = kBeamThreads >= 2 * kBeamMaxWidth ? kBeamMaxWidth : 0;   // thread kCascOff + u releases member u
   auto front_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kFront) : "memory"); };
+  if (!p.prefilter) {   // every symbol but the blank, in order
+    for (int i = tid; i < VW; i += kBeamThreads) {
+      unsigned m = (32 * i + 32 <= V) ? 0xffffffffu : ((1u << (V - 32 * i)) - 1u);
+      if ((p.blank >> 5) == i) m &= ~(1u << (p.blank & 31));
+      S.rmask[i] = m;
+    }
+  }
   raw_t pre[kBeamPre];
 #pragma unroll
   for (int k = 0; k < kBeamPre; k++) {
@@ -224,6 +242,64 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
       for (int c = tid; c < V; c += kFront) S.lp[c] = (double)raw[c];
     }
     front_sync();
+    if (p.prefilter) {
+      // ---- large alphabets: for a given member the extensions with an ordinary symbol rank by the symbol's log-probability,
+      //      so only the beam_width + 2 most probable symbols (the member's own last symbol and the space score differently)
+      //      plus the space can be among the beam_width best prefixes.  Their threshold by radix select over the row. --------
+      const int kR = min(WB + 2, V - 1);
+      unsigned long long rprefix = 0ull;
+      int rremaining = kR, shr = 56;
+      for (int i = tid; i < VW; i += kFront) S.rmask[i] = 0u;
+      for (; shr >= 0; shr -= 8) {
+        for (int i = tid; i < kBeamBins; i += kFront) S.hist[i] = 0u;
+        front_sync();
+        const unsigned long long pm = shr == 56 ? 0ull : (~0ull << (shr + 8));
+        for (int c = tid; c < V; c += kFront) {
+          if (c == p.blank) continue;
+          const unsigned long long k = beam_key(S.lp[c]);
+          if ((k & pm) == (rprefix & pm)) atomicAdd(&S.hist[(unsigned)(k >> shr) & 255u], 1u);
+        }
+        front_sync();
+        // every warp finds the bin on its own: the same registers everywhere, nothing to broadcast through shared memory
+        unsigned h[8], mine = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { h[j] = S.hist[lane * 8 + j]; mine += h[j]; }
+        unsigned above = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_down_sync(0xffffffffu, above, o); if (lane + o < 32) above += u; }
+        above -= mine;
+        const bool here = above < (unsigned)rremaining && above + mine >= (unsigned)rremaining;
+        unsigned acc = above, hd = h[0]; int d = 0;
+#pragma unroll
+        for (int j = 7; j > 0; j--) {
+          if (d == 0) { if (acc + h[j] >= (unsigned)rremaining) { d = j; hd = h[j]; } else acc += h[j]; }
+        }
+        const int src = __ffs(__ballot_sync(0xffffffffu, here)) - 1;
+        const int bin = __shfl_sync(0xffffffffu, lane * 8 + d, src);
+        const int need_r = __shfl_sync(0xffffffffu, rremaining - (int)acc, src);
+        const int cnt_r = __shfl_sync(0xffffffffu, (int)hd, src);
+        rprefix |= (unsigned long long)bin << shr;
+        rremaining = need_r;
+        front_sync();                       // the histogram is cleared again at the top
+        if (cnt_r == need_r || shr == 0) break;
+      }
+      const unsigned long long rcls = rprefix >> shr;
+      int nlist = 0;
+      for (int c0 = 0; c0 < V; c0 += kFront) {   // the list, in symbol order
+        const int c = c0 + tid;
+        const bool in = c < V && c != p.blank && ((beam_key(S.lp[c]) >> shr) >= rcls || c == p.space);
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        if (lane == 0) s_wcnt[warp] = __popc(m);
+        front_sync();
+        int off = nlist, tot = 0;
+#pragma unroll
+        for (int q = 0; q < kFront / 32; q++) { const int n = s_wcnt[q]; if (q < warp) off += n; tot += n; }
+        if (in) { S.rc[off + __popc(m & ((1u << lane) - 1u))] = c; atomicOr(&S.rmask[c >> 5], 1u << (c & 31)); }
+        nlist += tot;
+        front_sync();
+      }
+      if (tid == 0) s_nR = nlist;
+    }
 
     // ---- phase A: every member's own update (:372-376, :383-385) ----------------------------------------------
     if (tid < W) {
@@ -261,6 +337,9 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
     }
     __syncthreads();
     const int nz = min(s_nz2, WB);
+    const int nR = p.prefilter ? s_nR : V - 1;                      // symbols every member is extended with
+    const bool use_cache = CACHE && (long long)W * nR <= (long long)p.kc_cap;
+    auto sym = [&](int j) -> int { return p.prefilter ? S.rc[j] : j + (j >= p.blank ? 1 : 0); };   // j-th extended symbol
     // ---- phase B: extensions that find a living prefix (:244-246): a member of the beam takes the mass, a pruned prefix
     //      that a descendant keeps alive swallows it ---------------------------------------------------------------------------
     if (tid < W) {
@@ -277,11 +356,11 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
     if (tid < W) S.mkey[tid] = beam_key(beam_score(beam_lse(S.npnb[tid], S.npb[tid]), C.nw[tid], p.wip));
     {
       int excl = 0;
-      for (int i = tid; i < W * VW; i += kBeamThreads) excl += __popc(S.bitmap[i]);
+      for (int i = tid; i < W * VW; i += kBeamThreads) excl += __popc(S.bitmap[i] & S.rmask[i % VW]);
       excl = warp_sum(excl);
       if (lane == 0 && excl) atomicAdd(&s_excl, excl);
     }
-    if (CACHE) {
+    if (use_cache) {
       unsigned long long kmax = 0ull, kmin = ~0ull;
       if (tid < W) {
         // members take part in the range as well (mkey is this thread's own value)
@@ -291,16 +370,17 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
         const int last = C.last[s];
         const double base = S.full[s], baseb = C.pb[s];
         const double penx = S.penx[s], pens = S.pens[s];
-        for (int c0 = 0; c0 < V; c0 += 32) {
-          const int c = c0 + lane;
-          if (c < V) {
+        for (int j0 = 0; j0 < nR; j0 += 32) {
+          const int j = j0 + lane;
+          if (j < nR) {
+            const int c = sym(j);
             unsigned long long k = 0ull;
-            if (c != p.blank && !((S.bitmap[s * VW + (c0 >> 5)] >> lane) & 1u)) {
+            if (!((S.bitmap[s * VW + (c >> 5)] >> (c & 31)) & 1u)) {
               const double v = BEAM_EXT_VALUE(c, last, baseb, base);
               k = beam_key(__dsub_rn(__dadd_rn(v, 0.0), c == p.space ? pens : penx));
               kmax = k > kmax ? k : kmax; kmin = k < kmin ? k : kmin;
             }
-            S.kc[s * V + c] = k;
+            S.kc[s * nR + j] = k;
           }
         }
       }
@@ -312,7 +392,7 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
       if (lane == 0) { atomicMax(&s_kmax, kmax); atomicMin(&s_kmin, kmin); }
     }
     __syncthreads();
-    const int total = W + W * (V - 1) - s_excl;
+    const int total = W + W * nR - s_excl;
     // ---- phase D: radix select of the beam_width best (8-bit digits from the highest byte in which the keys differ) -------
     unsigned long long thr = 0ull;
     int sh = 0, need = total;
@@ -320,7 +400,7 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
       int remaining = WB;
       unsigned long long prefix = 0ull;
       int sh0 = kBeamTopShift;
-      if (CACHE) {
+      if (use_cache) {
         const unsigned long long diff = s_kmax ^ s_kmin;
         sh0 = diff ? ((63 - __clzll((long long)diff)) / kBeamDigit) * kBeamDigit : 0;
         prefix = sh0 + kBeamDigit >= 64 ? 0ull : (s_kmax & (~0ull << (sh0 + kBeamDigit)));
@@ -333,8 +413,8 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
           const unsigned long long k = S.mkey[tid];
           if ((k & pm) == (prefix & pm)) atomicAdd(&S.hist[(unsigned)(k >> sh) & (kBeamBins - 1)], 1u);
         }
-        if (CACHE) {
-          for (int i = tid; i < W * V; i += kBeamThreads) {
+        if (use_cache) {
+          for (int i = tid; i < W * nR; i += kBeamThreads) {
             const unsigned long long k = S.kc[i];
             if (k && (k & pm) == (prefix & pm)) atomicAdd(&S.hist[(unsigned)(k >> sh) & (kBeamBins - 1)], 1u);
           }
@@ -343,10 +423,10 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
             const int last = C.last[s];
             const double base = S.full[s], baseb = C.pb[s];
             const double penx = S.penx[s], pens = S.pens[s];
-            for (int c0 = 0; c0 < V; c0 += 32) {
-              const int c = c0 + lane;
-              bool valid = c < V && c != p.blank;
-              if (valid) valid = !((S.bitmap[s * VW + (c0 >> 5)] >> lane) & 1u);
+            for (int j0 = 0; j0 < nR; j0 += 32) {
+              const int j = j0 + lane;
+              const int c = j < nR ? sym(j) : 0;
+              bool valid = j < nR && !((S.bitmap[s * VW + (c >> 5)] >> (c & 31)) & 1u);
               unsigned long long k = 0ull;
               if (valid) {
                 const double v = BEAM_EXT_VALUE(c, last, baseb, base);
@@ -405,11 +485,12 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
       const double base = S.full[s], baseb = C.pb[s];
       const double penx = S.penx[s], pens = S.pens[s];
       int ngt = 0, neq = 0;
-      for (int c0 = 0; c0 < V; c0 += 32) {
-        const int c = c0 + lane;
+      for (int j0 = 0; j0 < nR; j0 += 32) {
+        const int j = j0 + lane;
+        const int c = j < nR ? sym(j) : 0;
         unsigned long long k = 0ull;
-        if (CACHE) { if (c < V) k = S.kc[s * V + c]; }
-        else if (c < V && c != p.blank && !((S.bitmap[s * VW + (c0 >> 5)] >> lane) & 1u)) {
+        if (use_cache) { if (j < nR) k = S.kc[s * nR + j]; }
+        else if (j < nR && !((S.bitmap[s * VW + (c >> 5)] >> (c & 31)) & 1u)) {
           const double v = BEAM_EXT_VALUE(c, last, baseb, base);
           k = beam_key(__dsub_rn(__dadd_rn(v, 0.0), c == p.space ? pens : penx));
         }
@@ -463,11 +544,12 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
       int gb = S.cgt[W + s], eb = S.ceq[W + s];
       const int pn = C.node[s], pd = C.dep[s];
       const int psl = new_slot(s);
-      for (int c0 = 0; c0 < V; c0 += 32) {
-        const int c = c0 + lane;
+      for (int j0 = 0; j0 < nR; j0 += 32) {
+        const int j = j0 + lane;
+        const int c = j < nR ? sym(j) : 0;
         unsigned long long k = 0ull;
-        if (CACHE) { if (c < V) k = S.kc[s * V + c]; }
-        else if (c < V && c != p.blank && !((S.bitmap[s * VW + (c0 >> 5)] >> lane) & 1u)) {
+        if (use_cache) { if (j < nR) k = S.kc[s * nR + j]; }
+        else if (j < nR && !((S.bitmap[s * VW + (c >> 5)] >> (c & 31)) & 1u)) {
           const double v = BEAM_EXT_VALUE(c, last, baseb, base);
           k = beam_key(__dsub_rn(__dadd_rn(v, 0.0), c == p.space ? pens : penx));
         }
@@ -536,7 +618,7 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
   for (int k = s_need + tid; k < p.T; k += kBeamThreads) out[k] = 0;
 }
 
-size_t beam_smem_bytes(int V, int WB, bool cache) {
+size_t beam_smem_bytes(int V, int WB, size_t kc_cap) {
   auto a16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
   const int VW = (V + 31) >> 5, Vp = (V + 1) & ~1;
   size_t n = 2 * a16(sizeof(double) * Vp);   // lp, raw
@@ -547,11 +629,25 @@ size_t beam_smem_bytes(int V, int WB, bool cache) {
   n += 2 * a16(4 * 2 * (size_t)WB);    // cgt, ceq
   n += a16((size_t)4 * WB * VW);
   n += a16(4 * (size_t)kBeamBins) + 2 * a16(8 * (size_t)WB);   // hist, penx, pens
-  if (cache) n += a16((size_t)8 * WB * V);
+  n += a16(4 * (size_t)V) + a16(4 * (size_t)VW);               // rc, rmask
+  n += a16(8 * kc_cap);
   return n;
 }
 
-bool beam_cached(int V, int WB) { return (long long)V * WB <= kBeamKeyCache; }
+constexpr size_t kBeamSmemLimit = 200 * 1024;
+// How a shape runs: the symbols extended per frame (all, or the beam_width + 2 most probable + the space for large alphabets)
+// and how many extension keys are cached in shared memory (0: recomputed in every pass).
+struct BeamMode { int prefilter; int kc_cap; size_t smem; bool ok; };
+BeamMode beam_mode(int V, int WB) {
+  BeamMode m{0, 0, 0, false};
+  const long long all = (long long)V * WB;
+  if (all <= kBeamKeyCache) { m.kc_cap = (int)all; }
+  else if (V - 1 >= WB + 3) { m.prefilter = 1; m.kc_cap = kBeamKeyCache; }
+  m.smem = beam_smem_bytes(V, WB, (size_t)m.kc_cap);
+  if (m.smem > kBeamSmemLimit && m.kc_cap) { m.kc_cap = 0; m.smem = beam_smem_bytes(V, WB, 0); }   // no room for the cache
+  m.ok = m.smem <= kBeamSmemLimit;
+  return m;
+}
 
 }  // namespace
 
@@ -561,8 +657,7 @@ size_t beam_workspace_bytes(const e2e_ctc_desc& d, int beam_width) {
 }
 
 bool beam_supported(const e2e_ctc_desc& d, int beam_width) {
-  return beam_width >= 1 && beam_width <= kBeamMaxWidth &&
-         beam_smem_bytes(d.alphabet, beam_width, beam_cached(d.alphabet, beam_width)) <= 200 * 1024;
+  return beam_width >= 1 && beam_width <= kBeamMaxWidth && beam_mode(d.alphabet, beam_width).ok;
 }
 
 int launch_beam(const e2e_ctc_desc& d, int beam_width, int space_idx, double wip, const void* logits, const void* in_len,
@@ -576,8 +671,12 @@ int launch_beam(const e2e_ctc_desc& d, int beam_width, int space_idx, double wip
   p.node_cap = (long long)d.max_frames * beam_width + 1;
   p.B = d.batch; p.T = d.max_frames; p.V = d.alphabet; p.blank = d.blank_idx; p.beam = beam_width; p.space = space_idx;
   p.from_logits = d.from_logits; p.wip = wip;
-  const bool cache = beam_cached(d.alphabet, beam_width);
-  const size_t smem = beam_smem_bytes(d.alphabet, beam_width, cache);
+  const BeamMode md = beam_mode(d.alphabet, beam_width);
+  static const int no_pref = []() { const char* v = getenv("E2E_CTC_BEAM_NOPREFILTER"); return (v && *v) ? atoi(v) : 0; }();   // tests / experiments
+  p.prefilter = no_pref ? 0 : md.prefilter;
+  p.kc_cap = (no_pref && md.prefilter) ? 0 : md.kc_cap;
+  const bool cache = p.kc_cap > 0;
+  const size_t smem = beam_smem_bytes(d.alphabet, beam_width, (size_t)p.kc_cap);
   int dev = 0, sms = 148;
   E2E_CUDA_TRY(cudaGetDevice(&dev));
   E2E_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
