@@ -33,6 +33,7 @@
 //
 // Arithmetic: fp64 log-space with the reference's two-argument log_sum_exp (src/utils/math_utils.h:8-16) and the score
 // expression of :311-315 evaluated in its order without fused multiply-adds.
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -113,12 +114,21 @@ struct BeamSmem {
 
 // NT threads per CTA: 512 when every utterance has an SM to itself (the frame chain is latency-bound: more warps hide more
 // of it), 256 for larger batches (several CTAs per SM)
+#ifdef BEAM_PROF
+__device__ long long g_beam_prof[16];
+#define BEAM_T(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long now_ = clock64(); g_beam_prof[k] += now_ - prof_t; prof_t = now_; } } while (0)
+#else
+#define BEAM_T(k) do { } while (0)
+#endif
 template <typename T, bool CACHE, int NT>
 __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
+#ifdef BEAM_PROF
+  long long prof_t = clock64();
+#endif
   constexpr int kBeamThreads = NT, kBeamWarps = NT / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned long long s_thr, s_kmax, s_kmin;
-  __shared__ int s_need, s_ties, s_excl, s_done, s_keepm, s_keepall, s_nz2, s_ovf, s_nR, s_wcnt[8];
+  __shared__ int s_need, s_ties, s_excl, s_done, s_nz2, s_ovf, s_nR, s_wcnt[8];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int V = p.V, WB = p.beam, VW = (V + 31) >> 5, Vp = (V + 1) & ~1;
   using raw_t = typename Elem<T>::acc_t;   // float for 32/16-bit inputs, double for f64
@@ -142,8 +152,8 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
 #pragma unroll
     for (int k = 0; k < 9; k++) { *cf[k] = reinterpret_cast<int*>(take(4 * WB)); *nf[k] = reinterpret_cast<int*>(take(4 * WB)); }
     S.nwx = reinterpret_cast<int*>(take(4 * WB));
-    S.cgt = reinterpret_cast<int*>(take(4 * 2 * WB));
-    S.ceq = reinterpret_cast<int*>(take(4 * 2 * WB));
+    S.cgt = reinterpret_cast<int*>(take(4 * (2 * WB + 4)));
+    S.ceq = reinterpret_cast<int*>(take(4 * (2 * WB + 4)));
     S.bitmap = reinterpret_cast<unsigned*>(take((size_t)4 * WB * VW));
     S.hist = reinterpret_cast<unsigned*>(take(4 * kBeamBins));
     S.penx = reinterpret_cast<double*>(take(8 * WB)); S.pens = reinterpret_cast<double*>(take(8 * WB));
@@ -195,6 +205,7 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
     return (kq > ptcls || (kq == ptcls && eb < pneed)) ? S.cgt[q] + min(eb, pneed) : -1;
   };
   for (int t = 0; t < Ti; t++) {
+    BEAM_T(8);
     // ---- members that left the beam last frame release their node; a node nobody holds releases its parent (off the
     //      critical path: see above) ----------------------------------------------------------------------------------------
     if (casc_n >= 0) {
@@ -317,6 +328,7 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
     }
     }   // front threads
     __syncthreads();   // the members' updates are done; so are last frame's releases
+    BEAM_T(0);
     // ---- the pruned prefixes that block an extension of a member THIS frame: pruned last frame or earlier, still alive
     //      (a descendant in the beam holds them), parent still in the beam.  N holds last frame's beam and list. ------------
     for (int i = tid; i < nz_prev; i += kBeamThreads) {
@@ -336,6 +348,7 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
       }
     }
     __syncthreads();
+    BEAM_T(1);
     const int nz = min(s_nz2, WB);
     const int nR = p.prefilter ? s_nR : V - 1;                      // symbols every member is extended with
     const bool use_cache = CACHE && (long long)W * nR <= (long long)p.kc_cap;
@@ -352,6 +365,7 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
     }
     for (int i = tid; i < nz; i += kBeamThreads) atomicOr(&S.bitmap[C.zp[i] * VW + (C.zc[i] >> 5)], 1u << (C.zc[i] & 31));
     __syncthreads();
+    BEAM_T(2);
     // ---- phase C: scores of the members and of the fresh extensions; how many prefixes are there now (:392-399) ------
     if (tid < W) S.mkey[tid] = beam_key(beam_score(beam_lse(S.npnb[tid], S.npb[tid]), C.nw[tid], p.wip));
     {
@@ -366,7 +380,10 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
         // members take part in the range as well (mkey is this thread's own value)
         kmax = S.mkey[tid]; kmin = kmax;
       }
-      for (int s = warp; s < W; s += kBeamWarps) {
+      // the warps that hold members have just spent a log-sum-exp (fp64 exp + log) on the member keys: with 16 warps
+      // the rows go to the other warps only
+      const int mw = kBeamWarps >= 16 ? min((W + 31) >> 5, kBeamWarps - 8) : 0;
+      for (int s = warp - mw; s < W && s >= 0; s += kBeamWarps - mw) {
         const int last = C.last[s];
         const double base = S.full[s], baseb = C.pb[s];
         const double penx = S.penx[s], pens = S.pens[s];
@@ -392,6 +409,7 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
       if (lane == 0) { atomicMax(&s_kmax, kmax); atomicMin(&s_kmin, kmin); }
     }
     __syncthreads();
+    BEAM_T(3);
     const int total = W + W * nR - s_excl;
     // ---- phase D: radix select of the beam_width best (8-bit digits from the highest byte in which the keys differ) -------
     unsigned long long thr = 0ull;
@@ -475,6 +493,7 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
       thr = prefix; need = remaining;
     }
     const unsigned long long tcls = thr >> sh;
+    BEAM_T(4);
     // ---- phase E: survivors per position group ---------------------------------------------------------------
     if (tid < W) {
       const unsigned long long kq = S.mkey[tid] >> sh;
@@ -501,25 +520,25 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
       if (lane == 0) { S.cgt[W + s] = ngt; S.ceq[W + s] = neq; }
     }
     __syncthreads();
-    if (warp == 0) {   // exclusive scan over the 2W position groups (members, then member rows)
-      int run_gt = 0, run_eq = 0;
+    BEAM_T(5);
+    if (warp < 2) {   // exclusive scans over the 2W position groups (members, then member rows): warp 0 the counts above
+      int* a = warp == 0 ? S.cgt : S.ceq;   // the cut, warp 1 those in the cut class; the totals go to entry 2W
+      int run = 0;
       for (int i0 = 0; i0 < 2 * W; i0 += 32) {
         const int i = i0 + lane;
-        int g = i < 2 * W ? S.cgt[i] : 0, e = i < 2 * W ? S.ceq[i] : 0;
-        int sg = g, se = e;
+        const int g = i < 2 * W ? a[i] : 0;
+        int sg = g;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int ug = __shfl_up_sync(0xffffffffu, sg, o), ue = __shfl_up_sync(0xffffffffu, se, o);
-          if (lane >= o) { sg += ug; se += ue; }
-        }
-        if (i < 2 * W) { S.cgt[i] = run_gt + sg - g; S.ceq[i] = run_eq + se - e; }
-        if (i == W - 1) s_keepm = run_gt + sg + min(run_eq + se, need);   // surviving members
-        run_gt += __shfl_sync(0xffffffffu, sg, 31); run_eq += __shfl_sync(0xffffffffu, se, 31);
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, sg, o); if (lane >= o) sg += u; }
+        if (i < 2 * W) a[i] = run + sg - g;
+        run += __shfl_sync(0xffffffffu, sg, 31);
       }
-      if (lane == 0) s_keepall = run_gt + min(run_eq, need);
+      if (lane == 0) a[2 * W] = run;
     }
     __syncthreads();
-    const int keepm = s_keepm, keepall = s_keepall, node0 = n_nodes;
+    BEAM_T(6);
+    // surviving members = everything before entry W; survivors in all = the totals
+    const int keepm = S.cgt[W] + min(S.ceq[W], need), keepall = S.cgt[2 * W] + min(S.ceq[2 * W], need), node0 = n_nodes;
     // slot of member q after this frame's prune, -1 when it leaves the beam
     auto new_slot = [&](int q) -> int {
       const unsigned long long kq = S.mkey[q] >> sh;
@@ -572,6 +591,7 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
       }
     }
     __syncthreads();
+    BEAM_T(7);
     // ---- carried into the next frame: the nodes to release, this frame's cut (slot of a member after the prune) ------
     {
       const int u = tid - kCascOff;
@@ -626,7 +646,7 @@ size_t beam_smem_bytes(int V, int WB, size_t kc_cap) {
   n += 4 * a16(8 * (size_t)WB);        // full, npb, npnb, mkey
   n += 18 * a16(4 * (size_t)WB);       // node, par, last, nw, dep, pslot, zn, zp, zc x 2
   n += a16(4 * (size_t)WB);            // nwx
-  n += 2 * a16(4 * 2 * (size_t)WB);    // cgt, ceq
+  n += 2 * a16(4 * (2 * (size_t)WB + 4));    // cgt, ceq (+ the totals)
   n += a16((size_t)4 * WB * VW);
   n += a16(4 * (size_t)kBeamBins) + 2 * a16(8 * (size_t)WB);   // hist, penx, pens
   n += a16(4 * (size_t)V) + a16(4 * (size_t)VW);               // rc, rmask
@@ -702,6 +722,16 @@ int launch_beam(const e2e_ctc_desc& d, int beam_width, int space_idx, double wip
   }
 #undef E2E_K8
 #undef E2E_K8_
+#ifdef BEAM_PROF
+  {
+    long long h[16];
+    cudaStreamSynchronize(s);
+    cudaMemcpyFromSymbol(h, g_beam_prof, sizeof(h));
+    fprintf(stderr, "[beam prof] cycles of CTA 0: head %lld | blocked-list %lld | B %lld | C %lld | select %lld | count %lld | scan %lld | write %lld | tail %lld\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8]);
+    long long z[16] = {0};
+    cudaMemcpyToSymbol(g_beam_prof, z, sizeof(z));
+  }
+#endif
   E2E_CUDA_TRY(cudaGetLastError());
   return E2E_OK;
 }
