@@ -13,7 +13,8 @@ targets_lengths) -> (losses, grads)``, the signature of the reference's pybind11
 * ``ref_engine()`` -- the UNMODIFIED reference C++ compiled by ``oracle/build_ref.py`` into
   ``oracle/_ref/`` (kind ``"reference"``); present when that directory travelled with the repo.
 
-``ctc_loss_module`` / ``greedy_decode`` restate the few Python lines the reference wraps around
+``beam_decode`` is the LM-free prefix beam search (decoders/ctc_decoder.py:76-115 over ctc_decoder.cpp:153-198,353-441)
+through the compiled reference or the C restatement.  ``ctc_loss_module`` / ``greedy_decode`` restate the few Python lines the reference wraps around
 its engines (pytorch_end2end/modules/ctc_loss.py:25-57, functions/forward_backward.py:6-35,
 decoders/ctc_decoder.py:117-149) so either engine can be driven exactly as the reference drives it.
 """

@@ -6,7 +6,7 @@
  * --impl reference legs use it, and only as the checker / the reported CPU baseline.
  *
  * Parity status: PINNED.  oracle/test vectors: the five known-answer losses of the reference's
- * tests/test_ctc.py:69-165, the greedy known answers of tests/test_ctc_decoder.py:44-59,86-166,
+ * tests/test_ctc.py:69-165, the greedy and prefix-beam known answers of tests/test_ctc_decoder.py:44-59,86-166,
  * and differential runs against the compiled, unmodified reference (oracle/_ref, built by
  * oracle/build_ref.py) -- see tests/test_oracle.py and tests/golden/.
  *
@@ -29,6 +29,13 @@
  *                                                              (_get_alignment_asg_1d), :109-138 (batch driver,
  *                                                              -100 fill); pinned by tests/golden/align_*.npz,
  *                                                              made by running the reference's numba code
+ *   ctc_oracle_beam()      <- src/decoders/ctc_decoder.cpp:153-198 (decode), :353-441 (decode_sentence), :241-309
+ *                                                              (get_next_prefix without a language model), :311-340
+ *                                                              (scores), :225-239 (get_sentence); the shared_ptr /
+ *                                                              weak_ptr ownership is restated with reference counts;
+ *                                                              pinned by tests/golden/beam_*.npz, made by running the
+ *                                                              compiled reference (make_beam_golden.py), and by a
+ *                                                              differential test wherever oracle/_ref travelled
  *
  * Storage is frame-major ([T][S]) here, where the reference keeps [S][T]; the arithmetic and the
  * order of the chained two-argument log-sum-exp calls are the reference's.
