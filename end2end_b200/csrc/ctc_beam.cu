@@ -70,7 +70,8 @@ static_assert(kBeamBins % 32 == 0 && kBeamBins <= 2048, "digit width");
 constexpr int kBeamPre = 4;        // symbols per thread of the next frame's row kept in flight (V <= 4 x threads)
 constexpr int kBeamKeyCache = 19200;   // extensions (beam x alphabet) whose keys are kept in shared memory (150 KB)
 
-__device__ __forceinline__ double beam_lse(double a, double b) {   // math_utils.h:8-16
+// (out of line on purpose: fp64 exp + log are ~400 instructions, and the frame loop must fit the instruction cache)
+__device__ __noinline__ double beam_lse(double a, double b) {   // math_utils.h:8-16
   if (a == -INFINITY) return b;
   if (b == -INFINITY) return a;
   if (a > b) return __dadd_rn(a, log(__dadd_rn(1.0, exp(__dsub_rn(b, a)))));
@@ -88,6 +89,10 @@ __device__ __forceinline__ unsigned long long beam_key(double x) {
   x = __dadd_rn(x, 0.0);
   const unsigned long long u = (unsigned long long)__double_as_longlong(x);
   return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+
+__device__ __forceinline__ double beam_unkey(unsigned long long k) {   // the score behind a key (k > 1)
+  return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
 }
 
 struct BeamBuf {          // one copy of the beam (+ the pruned prefixes that still block an extension of a member)
@@ -128,7 +133,7 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
   constexpr int kBeamThreads = NT, kBeamWarps = NT / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned long long s_thr, s_kmax, s_kmin;
-  __shared__ int s_need, s_ties, s_excl, s_done, s_nz2, s_ovf, s_nR, s_wcnt[8];
+  __shared__ int s_need, s_ties, s_excl, s_done, s_nz2, s_ovf, s_nR, s_wcnt[8], s_above, s_tie_now;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int V = p.V, WB = p.beam, VW = (V + 31) >> 5, Vp = (V + 1) & ~1;
   using raw_t = typename Elem<T>::acc_t;   // float for 32/16-bit inputs, double for f64
@@ -172,7 +177,7 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
     BeamNode r; r.parent = -1; r.chr = -1; r.refs = 1; r.depth = 0;
     nodes[0] = r;
     C.node[0] = 0; C.par[0] = -1; C.last[0] = -1; C.nw[0] = 0; C.dep[0] = 0; C.pslot[0] = -1; C.pb[0] = 0.0; C.pnb[0] = -INFINITY;
-    s_ties = 0; s_ovf = 0; s_nz2 = 0;
+    s_ties = 0; s_ovf = 0; s_nz2 = 0; s_tie_now = 0;
   }
   // The first kFront threads (8 warps) run the head of a frame -- staging the row, the log-softmax, the members' own
   // updates -- synchronising among themselves on a named barrier.  With 512 threads the other half spends that time
@@ -198,6 +203,7 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
 
   int W = 1, n_nodes = 1, nz_prev = 0, W_prev = 0;
   int casc_n = -1, casc_par = -1;                 // the node this thread releases at the top of the next frame
+  double cut_depth = -1.0;                        // how far below the best score the last frame's cut was (< 0: unknown)
   unsigned long long ptcls = 0ull; int psh = 0, pneed = 0;   // last frame's cut: slot of a member after that prune
   auto prev_slot = [&](int q) -> int {
     const unsigned long long kq = S.mkey[q] >> psh;
@@ -383,11 +389,11 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
       // the warps that hold members have just spent a log-sum-exp (fp64 exp + log) on the member keys: with 16 warps
       // the rows go to the other warps only
       const int mw = kBeamWarps >= 16 ? min((W + 31) >> 5, kBeamWarps - 8) : 0;
-      for (int s = warp - mw; s < W && s >= 0; s += kBeamWarps - mw) {
+            for (int s = warp - mw; s < W && s >= 0; s += kBeamWarps - mw) {
         const int last = C.last[s];
         const double base = S.full[s], baseb = C.pb[s];
         const double penx = S.penx[s], pens = S.pens[s];
-        for (int j0 = 0; j0 < nR; j0 += 32) {
+                      for (int j0 = 0; j0 < nR; j0 += 32) {
           const int j = j0 + lane;
           if (j < nR) {
             const int c = sym(j);
@@ -414,7 +420,104 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
     // ---- phase D: radix select of the beam_width best (8-bit digits from the highest byte in which the keys differ) -------
     unsigned long long thr = 0ull;
     int sh = 0, need = total;
-    if (total > WB) {
+    bool selected = false;
+    if (use_cache && total > WB && kBeamBins == 256 && cut_depth >= 0.0) {
+      // Fast path.  Shared-memory atomics retire about one per cycle per SM, so a histogram over all beam x V keys costs
+      // as many cycles as there are keys (measured: 5.4k of a 25k-cycle frame on c2).  The cut moves slowly relative to
+      // the best score, so only the keys within +-kWin of the PREDICTED cut (best score - last frame's depth) go into a
+      // 256-bin histogram (bins by integer key distance: monotone in the score); keys above the window are merely
+      // counted (ballots), keys below it ignored; the few keys of the boundary bin are then ranked exactly.  A wrong
+      // prediction (cut outside the window, boundary bin too full) falls back to the radix passes below: same result.
+      constexpr int kSelCap = 128;                          // 128 keys = the histogram's 1 KB, reused as the list
+      constexpr double kWin = 3.0;
+      const double smax = beam_unkey(s_kmax);
+      const unsigned long long hi_key = beam_key(smax - cut_depth + kWin), lo_key = beam_key(smax - cut_depth - kWin);
+      const unsigned long long span = hi_key - lo_key;
+      const int bshift = (span >> 8) ? (64 - __clzll((long long)span)) - 8 : 0;
+      for (int i = tid; i < 256; i += kBeamThreads) S.hist[i] = 0u;
+      if (tid == 0) { s_need = 0; s_done = 0; s_above = 0; }
+      __syncthreads();
+      if (hi_key > lo_key && lo_key > 1ull) {
+        int above = 0;
+        if (tid < W) {
+          const unsigned long long k = S.mkey[tid];
+          if (k > hi_key) above++; else if (k >= lo_key) atomicAdd(&S.hist[(unsigned)((hi_key - k) >> bshift)], 1u);
+        }
+        for (int i = tid; i < W * nR; i += kBeamThreads) {
+          const unsigned long long k = S.kc[i];
+          if (k > hi_key) above++; else if (k >= lo_key) atomicAdd(&S.hist[(unsigned)((hi_key - k) >> bshift)], 1u);
+        }
+        above = warp_sum(above);
+        if (lane == 0 && above) atomicAdd(&s_above, above);
+      }
+      __syncthreads();
+      BEAM_T(11);
+      if (warp == 0 && s_above < WB && hi_key > lo_key && lo_key > 1ull) {   // the bin that holds the beam_width-th best (bin 0 is the best)
+        const unsigned want = (unsigned)(WB - s_above);
+        unsigned h[8], mine = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { h[j] = S.hist[lane * 8 + j]; mine += h[j]; }
+        unsigned incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        const unsigned before = incl - mine;
+        if (before < want && incl >= want) {
+          unsigned run = before, acc = before, hd = 0; int d = -1;
+#pragma unroll
+          for (int j = 0; j < 8; j++) {     // first bin of this lane whose running count reaches what is wanted
+            if (d < 0 && run + h[j] >= want) { d = j; hd = h[j]; acc = run; }
+            run += h[j];
+          }
+          s_thr = (unsigned long long)(lane * 8 + d);       // boundary bin
+          s_need = (int)(want - acc);                        // how many of its keys survive
+          s_done = hd <= (unsigned)kSelCap ? 1 : 0;
+        }
+      }
+      __syncthreads();
+      BEAM_T(12);
+      if (s_done) {
+        const unsigned bbin = (unsigned)s_thr; const int bneed = s_need;
+        unsigned long long* sel = reinterpret_cast<unsigned long long*>(S.hist);
+        __syncthreads();                                    // everybody has read the verdict: the histogram becomes the list
+        if (tid == 0) s_above = 0;                          // (now the list length)
+        __syncthreads();
+        if (tid < W) {
+          const unsigned long long k = S.mkey[tid];
+          if (k <= hi_key && k >= lo_key && (unsigned)((hi_key - k) >> bshift) == bbin) sel[atomicAdd(&s_above, 1)] = k;
+        }
+                for (int i = tid; i < W * nR; i += kBeamThreads) {
+          const unsigned long long k = S.kc[i];
+          if (k <= hi_key && k >= lo_key && (unsigned)((hi_key - k) >> bshift) == bbin) sel[atomicAdd(&s_above, 1)] = k;
+        }
+        __syncthreads();
+        BEAM_T(13);
+        const int nsel = s_above;
+#ifdef BEAM_PROF
+        if (blockIdx.x == 0 && tid == 0) g_beam_prof[15] += nsel;
+#endif
+        if (tid < nsel) {   // exact rank inside the boundary bin
+          const unsigned long long k = sel[tid];
+          int gt = 0, eq = 0;
+          for (int j = 0; j < nsel; j++) { const unsigned long long o = sel[j]; gt += o > k; eq += o == k; }
+          if (gt < bneed && gt + eq >= bneed) {   // the bneed-th largest (threads holding an equal key agree)
+            s_thr = k; s_need = bneed - gt;
+            if (eq > bneed - gt) s_tie_now = 1;   // equal scores on both sides of the cut
+          }
+        }
+        __syncthreads();
+        BEAM_T(14);
+        thr = s_thr; sh = 0; need = s_need;
+        if (tid == 0 && s_tie_now) { s_ties++; s_tie_now = 0; }
+        selected = true;
+#ifdef BEAM_PROF
+        if (blockIdx.x == 0 && tid == 0) g_beam_prof[9] += 1;
+#endif
+      }
+    }
+    if (total > WB && !selected) {
+#ifdef BEAM_PROF
+      if (blockIdx.x == 0 && tid == 0) g_beam_prof[10] += 1;
+#endif
       int remaining = WB;
       unsigned long long prefix = 0ull;
       int sh0 = kBeamTopShift;
@@ -432,16 +535,16 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
           if ((k & pm) == (prefix & pm)) atomicAdd(&S.hist[(unsigned)(k >> sh) & (kBeamBins - 1)], 1u);
         }
         if (use_cache) {
-          for (int i = tid; i < W * nR; i += kBeamThreads) {
+                            for (int i = tid; i < W * nR; i += kBeamThreads) {
             const unsigned long long k = S.kc[i];
             if (k && (k & pm) == (prefix & pm)) atomicAdd(&S.hist[(unsigned)(k >> sh) & (kBeamBins - 1)], 1u);
           }
         } else {
-          for (int s = warp; s < W; s += kBeamWarps) {
+                        for (int s = warp; s < W; s += kBeamWarps) {
             const int last = C.last[s];
             const double base = S.full[s], baseb = C.pb[s];
             const double penx = S.penx[s], pens = S.pens[s];
-            for (int j0 = 0; j0 < nR; j0 += 32) {
+                          for (int j0 = 0; j0 < nR; j0 += 32) {
               const int j = j0 + lane;
               const int c = j < nR ? sym(j) : 0;
               bool valid = j < nR && !((S.bitmap[s * VW + (c >> 5)] >> (c & 31)) & 1u);
@@ -492,6 +595,10 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
       }
       thr = prefix; need = remaining;
     }
+    if (use_cache && total > WB) {   // the prediction for the next frame's fast path
+      const double depth = beam_unkey(s_kmax) - beam_unkey(thr > 1ull ? thr : 2ull);
+      cut_depth = (depth == depth && depth < 1e300) ? depth : -1.0;
+    }
     const unsigned long long tcls = thr >> sh;
     BEAM_T(4);
     // ---- phase E: survivors per position group ---------------------------------------------------------------
@@ -499,12 +606,12 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
       const unsigned long long kq = S.mkey[tid] >> sh;
       S.cgt[tid] = kq > tcls; S.ceq[tid] = kq == tcls;
     }
-    for (int s = warp; s < W; s += kBeamWarps) {
+        for (int s = warp; s < W; s += kBeamWarps) {
       const int last = C.last[s];
       const double base = S.full[s], baseb = C.pb[s];
       const double penx = S.penx[s], pens = S.pens[s];
       int ngt = 0, neq = 0;
-      for (int j0 = 0; j0 < nR; j0 += 32) {
+            for (int j0 = 0; j0 < nR; j0 += 32) {
         const int j = j0 + lane;
         const int c = j < nR ? sym(j) : 0;
         unsigned long long k = 0ull;
@@ -524,7 +631,7 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
     if (warp < 2) {   // exclusive scans over the 2W position groups (members, then member rows): warp 0 the counts above
       int* a = warp == 0 ? S.cgt : S.ceq;   // the cut, warp 1 those in the cut class; the totals go to entry 2W
       int run = 0;
-      for (int i0 = 0; i0 < 2 * W; i0 += 32) {
+            for (int i0 = 0; i0 < 2 * W; i0 += 32) {
         const int i = i0 + lane;
         const int g = i < 2 * W ? a[i] : 0;
         int sg = g;
@@ -556,14 +663,14 @@ __global__ void __launch_bounds__(NT, 1) ctc_beam_kernel(const BeamParams p) {
         N.pslot[ns] = sp >= 0 ? new_slot(sp) : -1;
       }
     }
-    for (int s = warp; s < W; s += kBeamWarps) {
+        for (int s = warp; s < W; s += kBeamWarps) {
       const int last = C.last[s];
       const double base = S.full[s], baseb = C.pb[s];
       const double penx = S.penx[s], pens = S.pens[s];
       int gb = S.cgt[W + s], eb = S.ceq[W + s];
       const int pn = C.node[s], pd = C.dep[s];
       const int psl = new_slot(s);
-      for (int j0 = 0; j0 < nR; j0 += 32) {
+            for (int j0 = 0; j0 < nR; j0 += 32) {
         const int j = j0 + lane;
         const int c = j < nR ? sym(j) : 0;
         unsigned long long k = 0ull;
@@ -727,7 +834,7 @@ int launch_beam(const e2e_ctc_desc& d, int beam_width, int space_idx, double wip
     long long h[16];
     cudaStreamSynchronize(s);
     cudaMemcpyFromSymbol(h, g_beam_prof, sizeof(h));
-    fprintf(stderr, "[beam prof] cycles of CTA 0: head %lld | blocked-list %lld | B %lld | C %lld | select %lld | count %lld | scan %lld | write %lld | tail %lld\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8]);
+    fprintf(stderr, "[beam prof] cycles of CTA 0: head %lld | blocked-list %lld | B %lld | C %lld | select %lld | count %lld | scan %lld | write %lld | tail %lld | fast selects %lld, radix selects %lld | fast path: histogram %lld, boundary %lld, collect %lld, rank %lld, keys in the boundary bins %lld\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], h[12], h[13], h[14], h[15]);
     long long z[16] = {0};
     cudaMemcpyToSymbol(g_beam_prof, z, sizeof(z));
   }
