@@ -124,28 +124,6 @@ ctc_row_stats_reg_kernel(const T* __restrict__ logits, long long stride_b, long 
       for (int k = 0; k < VEC; k++) v[j][k] = -INFINITY;
     }
   }
-  // The utterance's own symbols (<= 4 per lane: up to 127 labels + blank) are requested NOW, while the row is in flight:
-  // index -> logit is two dependent round trips that used to start only after the reduction (22 % of the kernel's samples).
-  constexpr int KG = 4;
-  acc_t xs[KG];
-  int gk[KG];            // emission column of each held symbol, -1: none
-  bool pre_gather = false;
-  if (em.emis != nullptr && em.Lmax < 32 * KG) {
-    const long long Ti = load_index(em.in_len, em.len_is64, b), Li = load_index(em.tgt_len, em.len_is64, b);
-    pre_gather = true;
-    const bool live = t < Ti && Li >= 0 && Li <= em.Lmax;
-#pragma unroll
-    for (int q = 0; q < KG; q++) {
-      const int k = lane + 32 * q;
-      gk[q] = -1; xs[q] = 0;
-      if (live && k <= (int)Li) {
-        const bool isb = k == (int)Li;
-        const long long sym = isb ? em.blank : load_index(em.targets, em.tgt_is64, (long long)b * em.ts_b + k);
-        gk[q] = isb ? em.Lmax : k;
-        if (sym >= 0 && sym < V) xs[q] = Elem<T>::load(x + sym); else gk[q] = -2 - gk[q];   // label outside the alphabet: emission 0
-      }
-    }
-  }
   acc_t m = -INFINITY;
   bool has_nan = false;
 #pragma unroll
@@ -164,14 +142,7 @@ ctc_row_stats_reg_kernel(const T* __restrict__ logits, long long stride_b, long 
   acc_t ls = log_acc(s);
   if (has_nan) { m = NAN; ls = NAN; }
   if (lane == 0) { stats[2 * row] = m; stats[2 * row + 1] = ls; }
-  if (pre_gather) {
-    double* er = em.emis + row * em.stride;
-#pragma unroll
-    for (int q = 0; q < KG; q++) {
-      if (gk[q] >= 0) er[gk[q]] = k1_emission(xs[q], m, ls, em.from_logits);
-      else if (gk[q] < -1) er[-2 - gk[q]] = 0.0;
-    }
-  } else if (em.emis != nullptr) k1_gather<T>(em, x, b, t, row, V, m, ls, lane);
+  if (em.emis != nullptr) k1_gather<T>(em, x, b, t, row, V, m, ls, lane);
 }
 
 template <typename T, int VEC>

@@ -57,6 +57,23 @@ if [ "$what" = "beam" ]; then         # the prefix-beam-search kernel (added lat
     tail -2 $out/san_${tool}_beam_c1.log
   done
 fi
+if [ "$what" = "late" ]; then         # kernels changed late in round 2: K1 (symbol prefetch), K3 (posterior prefetch), sweep c3
+  cap() {
+    local name=$1 regex=$2 skip=$3; shift 3
+    $NCU --set full --import-source on -k "regex:$regex" -s $skip -c 1 -f -o $out/$name "$@" > $out/$name.log 2>&1
+    if [ -f $out/$name.ncu-rep ]; then
+      ncu -i $out/$name.ncu-rep --page raw --csv > $out/$name.raw.csv 2>/dev/null
+      ncu -i $out/$name.ncu-rep --page source --csv --print-source cuda,sass > $out/$name.source.csv 2>/dev/null
+      python tools/ncu_summary.py $out/$name.raw.csv > $out/$name.summary.txt 2>&1
+      python tools/ncu_lines.py $out/$name.source.csv 30 > $out/$name.lines.txt 2>&1
+      rm -f $out/$name.source.csv $out/$name.ncu-rep $out/$name.raw.csv
+    fi
+  }
+  cap ncu_rowstats_c4  ctc_row_stats        2 python tools/run_one.py c4 4
+  cap ncu_general_c4   ctc_fused_kernel     2 python tools/run_one.py c4 4
+  cap ncu_grad_c4      ctc_grad_kernel      2 python tools/run_one.py c4 4
+  cap ncu_sweep_c3     ctc_sweep_kernel     2 python tools/run_one.py c3 4
+fi
 if [ "$what" = "refresh" ]; then      # kernels changed after the first capture of the round
   NCUO=$NCU
   cap() {
