@@ -11,8 +11,12 @@
 //   * the reference makes a Prefix object for each of the beam x (V-1) extensions of a frame and throws all but
 //     beam_width of them away (std::nth_element).  Here an extension is never materialised: its score is one add of
 //     the frame's log-probability to a per-member base, recomputed wherever it is needed;
-//   * the beam_width best of the beam members + extensions are found by an MSB-first radix select on an order-preserving
-//     64-bit image of the fp64 score (8-bit digits, stops as soon as a digit bin holds exactly what is still needed);
+//   * the beam_width best of the beam members + extensions are found on an order-preserving 64-bit image of the fp64
+//     score (kept in shared memory when beam x V fits): normally by ONE 256-bin histogram over the keys within +-3 nats of
+//     the predicted cut (the cut moves slowly relative to the frame's best score; keys above the window are only counted)
+//     and an exact ranking of the boundary bin's few keys; otherwise (first frames, cut outside the window, keys not
+//     cached) by an MSB-first radix select (8-bit digits from the highest byte in which the keys differ, stopping as soon
+//     as a digit bin holds exactly what is still needed).  Both select the same set;
 //   * large alphabets (beam x V beyond the key cache): for one member the extensions with an ordinary symbol rank by the
 //     symbol's log-probability alone, so only the beam_width + 2 most probable symbols of the frame (ties included; the
 //     member's own last symbol and the space score differently) plus the space can reach the beam_width best.  Their
@@ -23,7 +27,9 @@
 //
 // The reference finds an existing child through a weak_ptr in its parent (:244-246).  What that does is kept exactly:
 // the prefix trie lives in the caller's workspace with a reference count per node (one for membership of the beam, one per
-// living child = the shared_ptr holders `prefixes` and `Prefix::parent`), a child list per node, and
+// living child = the shared_ptr holders `prefixes` and `Prefix::parent`); the slot of every member's parent and the pruned
+// prefixes that still block an extension of a member (at most one per member) are kept in shared memory, so
+// the frame loop follows no pointers, and
 //   - an extension whose node is in the beam adds its mass to that member (is_new == false),
 //   - an extension whose node was pruned but is still referenced by a descendant in the beam is swallowed: that prefix
 //     cannot re-enter the beam while the descendant lives (a property of the reference, reproduced on purpose),
