@@ -249,3 +249,25 @@ def test_sharded_loss_gloo_world2(tmp_path):
             for p in parts:                                              # same global scalar on every rank
                 assert torch.allclose(p["loss"], ref.detach(), rtol=1e-6, atol=1e-6)
                 assert torch.allclose(p["grad"], leaf.grad[p["idx"]], rtol=1e-6, atol=1e-7)
+
+
+def test_beam_workspace_query_and_limits(lib_built):
+    """Host-only entry point of the prefix beam search: the size query works without a device and states its limits."""
+    import ctypes
+    from end2end_b200 import _lib
+    L = _lib.load()
+    d = _lib.Desc()
+    d.batch, d.max_frames, d.alphabet, d.max_targets = 64, 400, 29, 0
+    d.blank_idx, d.dtype = 0, _lib.E2E_F32
+    d.targets_itype = d.lengths_itype = _lib.E2E_I64
+    d.logits_stride_b, d.logits_stride_t = 400 * 29, 29
+    n = L.e2e_ctc_beam_workspace_bytes(ctypes.byref(d), 100)
+    nodes = 64 * (400 * 100 + 1) * 16                      # one 16-byte trie node per frame and beam slot, plus the root
+    assert nodes <= n < nodes + 256
+    assert L.e2e_ctc_beam_workspace_bytes(ctypes.byref(d), 257) == 0          # beam_width beyond the build's limit
+    assert "limits" in L.e2e_last_error_string().decode()
+    assert L.e2e_ctc_beam_workspace_bytes(ctypes.byref(d), 0) == 0
+    d.alphabet, d.logits_stride_t, d.logits_stride_b = 1024, 1024, 400 * 1024                # large alphabets are pre-filtered per frame
+    assert L.e2e_ctc_beam_workspace_bytes(ctypes.byref(d), 100) > 0
+    d.alphabet = 32768                                     # rows of this size do not fit shared memory
+    assert L.e2e_ctc_beam_workspace_bytes(ctypes.byref(d), 100) == 0
